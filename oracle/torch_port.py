@@ -1,0 +1,144 @@
+"""Torch-CPU port of the reference's eager code path -- TEST INFRASTRUCTURE ONLY.
+
+This is the timed CPU baseline (``cpu_baseline.kind == "port"``) and the
+``bench.py --impl reference`` arm: the reference tree is Python and cannot
+travel to the GPU box, so its eager op sequence is restated here with the same
+dense temporaries (the [G,P,2] corner tensors, the [G,P] IoU matrix, the two
+``max`` passes, the per-GT Python loop with one tensor index per iteration),
+the same per-image Python loop, and the same third-party NMS
+(``torchvision.ops.nms``, R/utils/utils_bbox.py:275-279), so that its cost on
+the host cores is the cost the reference pays with ``Cuda=False``.
+
+Checked bit-for-bit against the imported reference by tests/golden/make_golden.py
+(--check) in the dev container and against tests/golden/*.npz everywhere.
+"""
+import torch
+
+try:  # third-party NMS used by the reference (not vendored there, unpinned)
+    from torchvision.ops import nms as _tv_nms
+except Exception:  # pragma: no cover
+    _tv_nms = None
+
+
+def corners(p):
+    """(cx,cy,w,h) -> (x1,y1,x2,y2); R/nets/retinaface_training.py:8-10."""
+    half = p[:, 2:] / 2
+    return torch.cat((p[:, :2] - half, p[:, :2] + half), 1)
+
+
+def overlap_matrix(a, b):
+    """Dense IoU [A,B]; R/nets/retinaface_training.py:22-59 (materialises the
+    [A,B,2] corner temporaries like the reference's expand+min/max)."""
+    na, nb = a.size(0), b.size(0)
+    hi = torch.min(a[:, None, 2:].expand(na, nb, 2), b[None, :, 2:].expand(na, nb, 2))
+    lo = torch.max(a[:, None, :2].expand(na, nb, 2), b[None, :, :2].expand(na, nb, 2))
+    d = torch.clamp(hi - lo, min=0)
+    inter = d[:, :, 0] * d[:, :, 1]
+    area_a = ((a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]))[:, None].expand_as(inter)
+    area_b = ((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]))[None, :].expand_as(inter)
+    return inter / (area_a + area_b - inter)
+
+
+def encode_boxes(m, p, var):
+    """R/nets/retinaface_training.py:61-70."""
+    c = (m[:, :2] + m[:, 2:]) / 2 - p[:, :2]
+    c /= (var[0] * p[:, 2:])
+    s = torch.log((m[:, 2:] - m[:, :2]) / p[:, 2:]) / var[1]
+    return torch.cat([c, s], 1)
+
+
+def encode_points(m, p, var):
+    """R/nets/retinaface_training.py:72-84 (builds the [P,5,4] prior temporary)."""
+    n = m.size(0)
+    pts = m.reshape(n, 5, 2)
+    pp = torch.cat([p[:, k][:, None].expand(n, 5)[:, :, None] for k in range(4)], dim=2)
+    c = pts - pp[:, :, :2]
+    c /= (var[0] * pp[:, :, 2:])
+    return c.reshape(n, -1)
+
+
+def assign_one(thr, truths, priors, var, labels, landms, loc_t, conf_t, landm_t, idx,
+               label_mode=0, encode_mode=1):
+    """One image of ``match``; R/nets/retinaface_training.py:93-162."""
+    ov = overlap_matrix(truths, corners(priors))
+    _, bp_idx = ov.max(1, keepdim=True)
+    bp_idx.squeeze_(1)
+    bt_ov, bt_idx = ov.max(0, keepdim=True)
+    bt_idx.squeeze_(0)
+    bt_ov.squeeze_(0)
+    bt_ov.index_fill_(0, bp_idx, 2)
+    for j in range(bp_idx.size(0)):           # sequential, last j wins (:129-130)
+        bt_idx[bp_idx[j]] = j
+    m = truths[bt_idx]
+    c = labels[bt_idx]
+    if label_mode:
+        c = c + 1                             # R/utils/box_utils.py:315
+    c[bt_ov < thr] = 0
+    loc_t[idx] = encode_boxes(m, priors, var) if encode_mode else m
+    conf_t[idx] = c
+    if landm_t is not None:
+        landm_t[idx] = encode_points(landms[bt_idx], priors, var)
+    return bt_idx, bt_ov, bp_idx
+
+
+def assign_batch(thr, targets, priors, var):
+    """The loop of MultiBoxLoss.forward, R/nets/retinaface_training.py:197-214."""
+    n, P = len(targets), priors.size(0)
+    loc_t = torch.Tensor(n, P, 4)
+    landm_t = torch.Tensor(n, P, 10)
+    conf_t = torch.LongTensor(n, P)
+    for i in range(n):
+        t = targets[i]
+        assign_one(thr, t[:, :4], priors, var, t[:, -1], t[:, 4:14], loc_t, conf_t, landm_t, i)
+    return loc_t, conf_t, landm_t
+
+
+def decode_boxes(loc, p, var):
+    """R/utils/utils_bbox.py:29-34."""
+    b = torch.cat((p[:, :2] + loc[:, :2] * var[0] * p[:, 2:],
+                   p[:, 2:] * torch.exp(loc[:, 2:] * var[1])), 1)
+    b[:, :2] -= b[:, 2:] / 2
+    b[:, 2:] += b[:, :2]
+    return b
+
+
+def decode_points(pre, p, var):
+    """R/utils/utils_bbox.py:39-46."""
+    return torch.cat([p[:, :2] + pre[:, 2 * k:2 * k + 2] * var[0] * p[:, 2:] for k in range(5)], dim=1)
+
+
+def suppress(detection, conf_thres=0.5, nms_thres=0.3):
+    """``non_max_suppression``; R/utils/utils_bbox.py:260-296."""
+    detection = detection[detection[:, 4] >= conf_thres]
+    if len(detection) <= 0:
+        return []
+    keep = _tv_nms(detection[:, :4], detection[:, 4], nms_thres)
+    return detection[keep].cpu().numpy()
+
+
+def infer_one(loc, conf, landm, priors, var, conf_thres=0.5, nms_thres=0.3):
+    """Per-image post-processing of Retinaface.detect_image, R/predict.py:167-181."""
+    boxes = decode_boxes(loc, priors, var)
+    score = conf[:, 1:2]
+    pts = decode_points(landm, priors, var)
+    return suppress(torch.cat([boxes, score, pts], -1), conf_thres, nms_thres)
+
+
+def infer_one_topk(loc, conf, landm, priors, var, conf_thres=0.02, pre_nms_topk=5000, nms_thres=0.4,
+                   keep_topk=750):
+    """cfg3's composed pipeline: decode -> score > thr -> stable
+    descending sort[:topk] -> torchvision nms -> [:keep_topk].  Returns
+    (dets [K,15], prior indices [K])."""
+    boxes = decode_boxes(loc, priors, var)
+    pts = decode_points(landm, priors, var)
+    s = conf[:, 1]
+    idx = torch.nonzero(s > conf_thres).squeeze(1)
+    order = torch.sort(s[idx], stable=True, descending=True)[1]
+    if pre_nms_topk > 0:
+        order = order[:pre_nms_topk]
+    idx = idx[order]
+    keep = _tv_nms(boxes[idx], s[idx], nms_thres)
+    if keep_topk > 0:
+        keep = keep[:keep_topk]
+    idx = idx[keep]
+    return torch.cat([boxes[idx], s[idx, None], pts[idx]], 1), idx
