@@ -1,0 +1,169 @@
+/*
+ * jabd_b200.h -- C-ABI of libjabd_b200.so: the JABD box-geometry hot path on B200 (sm_100a).
+ *
+ * The reference (R/ = JABD2080ti/, pure Python/PyTorch) has no FFI of its own; its boundary for this
+ * path is a set of Python functions.  Each entry point below names the reference function(s) it
+ * replaces (R/file:line); the Python package `jabd_b200` re-exports them under the reference's names.
+ *
+ * Conventions
+ *   - Every pointer is DEVICE memory on the current CUDA device unless the name ends in `_host`.
+ *   - fp32 data, C-contiguous.  `conf_t` is int64 (torch.LongTensor, R/nets/retinaface_training.py:199).
+ *   - The caller owns every buffer, including the workspace; the library never allocates or frees
+ *     device memory, keeps no pointer after return and has no global mutable state.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises unless
+ *     its comment says so.  Calls are re-entrant and may run concurrently on distinct streams.
+ *   - Return 0 on success or a negative JABD_E* code; `jabd_last_error()` gives a thread-local message.
+ *   - There is no CPU implementation behind any of these symbols.
+ */
+#ifndef JABD_B200_H
+#define JABD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define JABD_API __attribute__((visibility("default")))
+#else
+#define JABD_API
+#endif
+
+typedef void *jabd_stream_t; /* cudaStream_t */
+
+enum {
+    JABD_OK = 0,
+    JABD_EINVAL = -1,    /* bad argument (null pointer, negative size, unsupported option) */
+    JABD_EALIGN = -2,    /* pointer not aligned as documented */
+    JABD_EWORKSPACE = -3,/* workspace missing or too small */
+    JABD_ECUDA = -4,     /* a CUDA runtime call failed; see jabd_last_error() */
+    JABD_ENODEVICE = -5  /* no sm_100 device */
+};
+
+/* GT row layout of the reference data loader (R/utils/dataloader.py:37-58):
+ * x1 y1 x2 y2 | 5 x (lx, ly) | label, normalised to [0,1]. */
+#define JABD_GT_ROW 15
+#define JABD_DET_ROW 15 /* x1 y1 x2 y2 score | 5 x (lx, ly)   (R/predict.py:180) */
+
+/* label_mode: 0 = live training match, conf = label          (R/nets/retinaface_training.py:137)
+ *             1 = SSD-legacy match,    conf = label + 1      (R/utils/box_utils.py:315)            */
+/* encode_mode: 1 = SSD encode of the matched box             (R/nets/retinaface_training.py:148)
+ *              0 = raw matched x1y1x2y2 (match_iou/_ious)    (R/nets/retinaface_training_DIOU.py:229,
+ *                                                             R/utils/box_utils.py:229-273)         */
+/* flags for jabd_assign */
+#define JABD_ASSIGN_DENSE 1 /* evaluate every prior x GT pair (no spatial culling); same results */
+
+JABD_API int jabd_version(void);
+JABD_API const char *jabd_last_error(void);
+/* Fills SM count and compute capability of the current device.  Synchronous, host only. */
+JABD_API int jabd_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- P1: prior boxes.  Replaces Anchors.get_anchors / Anchors_eval.get_anchors (R/utils/anchors.py:9-42,
+ * :43-79).  steps_host[n_levels]; min_sizes_host[sizes_off_host[n_levels]] grouped per level by
+ * sizes_off_host[n_levels+1].  Output [P,4] (cx,cy,w,h), float64 arithmetic rounded once to fp32, optional
+ * clamp to [0,1]. */
+JABD_API int64_t jabd_priors_count(const int *steps_host, const int *sizes_off_host, int n_levels, int H, int W);
+JABD_API int jabd_priors(const int *steps_host, const double *min_sizes_host, const int *sizes_off_host, int n_levels,
+                         int H, int W, int clip, float *out, int64_t P, jabd_stream_t stream);
+
+/* ---- M1/M2/E1/E2/D1/D2 as stand-alone operators (the reference's public helpers) -------------------- */
+/* point_form (R/nets/retinaface_training.py:8-10): [n,4] cxcywh -> [n,4] x1y1x2y2. */
+JABD_API int jabd_point_form(const float *boxes, int64_t n, float *out, jabd_stream_t stream);
+/* jaccard (R/nets/retinaface_training.py:41-59): dense IoU [A,B]; both inputs point-form. */
+JABD_API int jabd_jaccard(const float *box_a, int64_t A, const float *box_b, int64_t B, float *out, jabd_stream_t stream);
+/* intersect (R/nets/retinaface_training.py:22-39): dense intersection areas [A,B]. */
+JABD_API int jabd_intersect(const float *box_a, int64_t A, const float *box_b, int64_t B, float *out, jabd_stream_t stream);
+/* encode (R/nets/retinaface_training.py:61-70) and encode_landm (:72-84), n rows each. */
+JABD_API int jabd_encode(const float *matched, const float *priors, int64_t n, float var0, float var1, float *out,
+                         jabd_stream_t stream);
+JABD_API int jabd_encode_landm(const float *matched, const float *priors, int64_t n, float var0, float *out,
+                               jabd_stream_t stream);
+/* decode (R/utils/utils_bbox.py:29-34) and decode_landm (:39-46).  `batch` images share `priors` [P,4];
+ * loc is [batch,P,4] / pre is [batch,P,10]. */
+JABD_API int jabd_decode(const float *loc, const float *priors, int64_t P, int batch, float var0, float var1, float *out,
+                         jabd_stream_t stream);
+JABD_API int jabd_decode_landm(const float *pre, const float *priors, int64_t P, int batch, float var0, float *out,
+                               jabd_stream_t stream);
+
+/* ---- T1/T2: batched target assignment.  Replaces the per-image loop of MultiBoxLoss.forward
+ * (R/nets/retinaface_training.py:197-214) and match() (:93-162; SSD form R/utils/box_utils.py:276-320;
+ * match_iou R/nets/retinaface_training_DIOU.py:176-246).
+ *   priors [P,4] cxcywh, shared by the batch.
+ *   gt [sumG,15] packed rows, gt_off [B+1] int32 image offsets (device).  An image with no GT gets
+ *   all-zero targets (the reference's data loader never emits one, R/utils/dataloader.py:181-182).
+ *   loc_t [B,P,4] f32, conf_t [B,P] i64, landm_t [B,P,10] f32 (NULL: skip, 8-arg SSD forms).
+ *   Optional (NULL to skip): best_truth_idx [B,P] i32 and best_truth_overlap [B,P] f32 after the
+ *   force-match override (:127-130), best_prior_idx [sumG] i32 / best_prior_overlap [sumG] f32 (:111).
+ * Workspace: jabd_assign_workspace_bytes(), 256-byte aligned. */
+JABD_API size_t jabd_assign_workspace_bytes(int B, int64_t P, int64_t sumG);
+JABD_API int jabd_assign(const float *priors, int64_t P, const float *gt, const int *gt_off, int B, int64_t sumG,
+                         float threshold, float var0, float var1, int label_mode, int encode_mode, int flags,
+                         float *loc_t, int64_t *conf_t, float *landm_t, int *best_truth_idx, float *best_truth_overlap,
+                         int *best_prior_idx, float *best_prior_overlap, void *workspace, size_t workspace_bytes,
+                         jabd_stream_t stream);
+/* The two phases of jabd_assign, exposed for per-kernel timing (bench.py roofline) and tests:
+ * _match  = GT staging + IoU + both argmaxes into the workspace; _encode = force-match + gather + encode. */
+JABD_API int jabd_assign_match(const float *priors, int64_t P, const float *gt, const int *gt_off, int B, int64_t sumG,
+                               int flags, void *workspace, size_t workspace_bytes, jabd_stream_t stream);
+JABD_API int jabd_assign_encode(const float *priors, int64_t P, const float *gt, const int *gt_off, int B, int64_t sumG,
+                                float threshold, float var0, float var1, int label_mode, int encode_mode, float *loc_t,
+                                int64_t *conf_t, float *landm_t, int *best_truth_idx, float *best_truth_overlap,
+                                int *best_prior_idx, float *best_prior_overlap, void *workspace, size_t workspace_bytes,
+                                jabd_stream_t stream);
+/* Same call with HOST buffers (pageable or pinned): copies gt/gt_off in, runs jabd_assign, copies the
+ * three target tensors out.  priors and the staging area stay on the device:
+ * dev_scratch must hold jabd_assign_host_scratch_bytes().  Synchronises `stream` before returning. */
+JABD_API size_t jabd_assign_host_scratch_bytes(int B, int64_t P, int64_t sumG, int with_landm);
+JABD_API int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, const int *gt_off_host, int B,
+                              float threshold, float var0, float var1, int label_mode, int encode_mode, int flags,
+                              float *loc_t_host, int64_t *conf_t_host, float *landm_t_host, void *dev_scratch,
+                              size_t dev_scratch_bytes, jabd_stream_t stream);
+
+/* ---- S1/K1/N1/N2: score threshold, top-k, greedy NMS ---------------------------------------------- */
+/* thresh_mode: 0 = none, 1 = score >= conf_thres (R/utils/utils_bbox.py:266), 2 = score > conf_thres. */
+/* nms_mode: 0 = torchvision.ops.nms semantics (call site R/utils/utils_bbox.py:275-279): stable descending
+ *               order, suppress iff (double)(inter/((area_i+area_j)-inter)) > nms_thres;
+ *           1 = SSD-legacy nms / nms_r (R/utils/box_utils.py:384-448, R/utils/utils_bbox.py:116-180): ascending
+ *               order picked from the end (ties: higher index first), union = (area_j-inter)+area_i,
+ *               survive iff IoU <= (float)nms_thres.                                                  */
+
+/* Segmented top-k (K1; stable descending order, ties -> lower index).  scores[s*seg_stride + i*elem_stride],
+ * i < N, for s < S segments; out_idx [S,K] i32 (padding -1), out_count [S]. */
+JABD_API size_t jabd_topk_workspace_bytes(int S, int64_t N, int K);
+JABD_API int jabd_topk(const float *scores, int64_t seg_stride, int64_t elem_stride, int S, int64_t N, float conf_thres,
+                       int thresh_mode, int K, int *out_idx, int *out_count, void *workspace, size_t workspace_bytes,
+                       jabd_stream_t stream);
+
+/* Greedy NMS over S segments of N pre-decoded boxes.  boxes[s*box_seg_stride + i*box_stride + 0..3] x1y1x2y2,
+ * scores[s*score_seg_stride + i*score_stride].  pre_nms_topk <= 0: uncapped.  keep_idx [S,keep_cap] i32 in
+ * the reference's output order (padding -1), keep_count [S].  Only the first keep_cap keeps are produced. */
+JABD_API size_t jabd_nms_workspace_bytes(int S, int64_t N, int keep_cap);
+JABD_API int jabd_nms(const float *boxes, int64_t box_seg_stride, int64_t box_stride, const float *scores,
+                      int64_t score_seg_stride, int64_t score_stride, int S, int64_t N, float conf_thres, int thresh_mode,
+                      int pre_nms_topk, double nms_thres, int nms_mode, int keep_cap, int *keep_idx, int *keep_count,
+                      void *workspace, size_t workspace_bytes, jabd_stream_t stream);
+
+/* Fused inference post-processing for a batch (R/predict.py:167-181 composed per SURVEY D4):
+ * class-1 score (conf[:,1]) -> threshold -> top-k -> decode of the candidates -> NMS -> first keep_cap rows
+ * [x1 y1 x2 y2 score | decode_landm] (zero padded), prior indices (padding -1) and counts.
+ * loc [B,P,4], conf [B,P,2], landm [B,P,10] (NULL: landmark columns are zero), priors [P,4]. */
+JABD_API size_t jabd_detect_workspace_bytes(int B, int64_t P, int keep_cap);
+JABD_API int jabd_detect(const float *loc, const float *conf, const float *landm, const float *priors, int B, int64_t P,
+                         float var0, float var1, float conf_thres, int thresh_mode, int pre_nms_topk, double nms_thres,
+                         int keep_cap, float *dets, int *counts, int *keep_idx, void *workspace, size_t workspace_bytes,
+                         jabd_stream_t stream);
+/* Same with HOST buffers: loc/conf/landm in, dets/counts/keep_idx out; priors stay on the device.
+ * Synchronises `stream` before returning. */
+JABD_API size_t jabd_detect_host_scratch_bytes(int B, int64_t P, int keep_cap, int with_landm);
+JABD_API int jabd_detect_host(const float *loc_host, const float *conf_host, const float *landm_host,
+                              const float *priors_dev, int B, int64_t P, float var0, float var1, float conf_thres,
+                              int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap, float *dets_host,
+                              int *counts_host, int *keep_idx_host, void *dev_scratch, size_t dev_scratch_bytes,
+                              jabd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JABD_B200_H */

@@ -1,0 +1,100 @@
+"""ctypes binding of ``libjabd_b200.so`` (C-ABI declared in ``include/jabd_b200.h``).
+
+The library is the product: if it is missing or does not export a declared
+symbol the import of any operator module fails loudly -- there is no Python or
+CPU fallback anywhere in this package.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libjabd_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+c_int, c_i64, c_f32, c_f64, c_sz, c_vp = (ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
+                                          ctypes.c_size_t, ctypes.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/jabd_b200.h one to one
+SIGNATURES = {
+    "jabd_version": (c_int, []),
+    "jabd_last_error": (ctypes.c_char_p, []),
+    "jabd_device_info": (c_int, [c_vp, c_vp, c_vp]),
+    "jabd_priors_count": (c_i64, [c_vp, c_vp, c_int, c_int, c_int]),
+    "jabd_priors": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp]),
+    "jabd_point_form": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "jabd_jaccard": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "jabd_intersect": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "jabd_encode": (c_int, [c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp]),
+    "jabd_encode_landm": (c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp]),
+    "jabd_decode": (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_vp, c_vp]),
+    "jabd_decode_landm": (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp]),
+    "jabd_assign_workspace_bytes": (c_sz, [c_int, c_i64, c_i64]),
+    "jabd_assign": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_int,
+                            c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_assign_match": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_sz, c_vp]),
+    "jabd_assign_encode": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int,
+                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_assign_host_scratch_bytes": (c_sz, [c_int, c_i64, c_i64, c_int]),
+    "jabd_assign_host": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_int, c_int, c_int,
+                                 c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_topk_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
+    "jabd_topk": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_nms_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
+    "jabd_nms": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_i64, c_f32, c_int, c_int, c_f64, c_int,
+                         c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_detect_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
+    "jabd_detect": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64, c_int,
+                            c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_detect_host_scratch_bytes": (c_sz, [c_int, c_i64, c_int, c_int]),
+    "jabd_detect_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64,
+                                 c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+}
+
+ERRORS = {-1: ValueError, -2: ValueError, -3: ValueError, -4: RuntimeError, -5: RuntimeError}
+
+_lib = None
+
+
+def build(force=False, verbose=False):
+    """Compile ``libjabd_b200.so`` for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "jabd_b200.h"))
+    stale = force or not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
+    if stale:
+        cmd = ["make", "-C", CSRC, "-j4"] + ([] if verbose else ["-s"])
+        if force:
+            subprocess.check_call(["make", "-C", CSRC, "-s", "clean"])
+        subprocess.check_call(cmd)
+    return SO_PATH
+
+
+def lib():
+    """The loaded library; raises ``RuntimeError`` if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                "libjabd_b200.so is missing at %s: build it with `python -c \"import __graft_entry__ as g; g.build()\"` "
+                "(or `make -C %s`).  This package has no CPU or PyTorch fallback." % (SO_PATH, CSRC))
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().jabd_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise ERRORS.get(rc, RuntimeError)("%s failed (%d): %s" % (what or "libjabd_b200", rc, last_error()))
+
+
+def call(name, *args):
+    """Call an int-returning entry point and raise on a negative code."""
+    check(getattr(lib(), name)(*args), name)

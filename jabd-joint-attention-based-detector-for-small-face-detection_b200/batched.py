@@ -1,0 +1,223 @@
+"""Batched entry points of the hot path (additive to the reference's per-image API).
+
+``assign_targets`` replaces the per-image Python loop of ``MultiBoxLoss.forward``
+(R/nets/retinaface_training.py:197-227: CPU target tensors, one ``match`` per
+image, three D2H copies per image, three H2D copies per batch) with three kernel
+launches for the whole batch, outputs left on the GPU.
+
+``detect`` replaces the per-image post-processing of ``Retinaface.detect_image``
+(R/predict.py:167-181: decode, decode_landm, cat, threshold, torchvision NMS,
+``.cpu()``) with one launch for the whole batch.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, _tensor
+from ._tensor import ptr
+
+__all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "detect_host"]
+
+THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
+FLAG_DENSE = 1
+
+
+def pack_targets(targets, device):
+    """list of per-image ``[G_i, 15]`` arrays/tensors (R/utils/dataloader.py:177-186) or a
+    ``(gt_packed [sumG,15], gt_offsets [B+1])`` pair -> (gt CUDA f32 [sumG,15], offsets CUDA i32 [B+1],
+    host offsets list)."""
+    if isinstance(targets, tuple) and len(targets) == 2 and not isinstance(targets[0], (list, tuple)) \
+            and getattr(targets[1], "ndim", 1) == 1 and getattr(targets[0], "ndim", 0) == 2:
+        gt = _tensor.to_dev(targets[0], device)
+        offs_in = targets[1]
+        offs_host = [int(v) for v in (offs_in.tolist() if hasattr(offs_in, "tolist") else list(offs_in))]
+        offs = _tensor.to_dev(offs_in, device, torch.int32)
+    else:
+        rows = list(targets)
+        offs_host = [0]
+        for t in rows:
+            if t.ndim != 2 or t.shape[1] != 15:
+                raise ValueError("each target must be [G, 15] (x1 y1 x2 y2, 10 landmark coords, label)")
+            offs_host.append(offs_host[-1] + int(t.shape[0]))
+        if rows and all(isinstance(t, np.ndarray) for t in rows):
+            gt = _tensor.to_dev(np.concatenate(rows, 0) if rows else np.zeros((0, 15), np.float32), device)
+        elif rows:
+            gt = torch.cat([_tensor.to_dev(t, device) for t in rows], 0).contiguous()
+        else:
+            gt = torch.zeros((0, 15), dtype=torch.float32, device=device)
+        offs = torch.tensor(offs_host, dtype=torch.int32).to(device, non_blocking=True)
+    if gt.ndim != 2 or gt.shape[1] != 15:
+        raise ValueError("gt_packed must be [sumG, 15]")
+    if offs_host[0] != 0 or offs_host[-1] != gt.shape[0] or any(b < a for a, b in zip(offs_host, offs_host[1:])):
+        raise ValueError("gt_offsets must start at 0, be non-decreasing and end at sumG")
+    return gt, offs, offs_host
+
+
+def assign_targets(priors, targets, threshold=0.35, variances=(0.1, 0.2), label_mode=0, encode=True, dense=False,
+                   with_landm=True, return_match=False, allow_empty=False, out=None):
+    """Target assignment for a batch.
+
+    priors   [P,4] (cx,cy,w,h); targets: see ``pack_targets``.
+    Returns ``(loc_t [B,P,4] f32, conf_t [B,P] i64, landm_t [B,P,10] f32 | None)`` on the GPU and, with
+    ``return_match``, a dict with best_truth_idx/overlap ``[B,P]`` (after the force-match override) and
+    best_prior_idx/overlap ``[sumG]``.  ``out=(loc_t, conf_t, landm_t)`` writes into existing CUDA tensors.
+    An image without GT raises ``ValueError`` like the reference's ``max`` over an empty dim
+    (R/nets/retinaface_training.py:111) unless ``allow_empty`` (then its targets are all zero).
+    """
+    dev = _tensor.device_of(priors, targets[0] if isinstance(targets, (list, tuple)) and len(targets) else None)
+    pri = _tensor.to_dev(priors, dev)
+    if pri.ndim != 2 or pri.shape[1] != 4:
+        raise ValueError("priors must be [P, 4]")
+    gt, offs, offs_host = pack_targets(targets, dev)
+    B, P, sumG = len(offs_host) - 1, int(pri.shape[0]), int(gt.shape[0])
+    if not allow_empty and any(b == a for a, b in zip(offs_host, offs_host[1:])):
+        raise ValueError("assign_targets: an image has no ground truth (the reference raises on max over an empty dim)")
+    v0, v1 = _tensor.variances_of(variances)
+    if out is not None:
+        loc_t, conf_t, landm_t = out
+        for t, shp, dt in ((loc_t, (B, P, 4), torch.float32), (conf_t, (B, P), torch.int64)):
+            if not (t.is_cuda and t.is_contiguous() and tuple(t.shape) == shp and t.dtype == dt):
+                raise ValueError("out tensors must be contiguous CUDA tensors of shape [B,P,4] f32 / [B,P] i64 / [B,P,10] f32")
+        if landm_t is not None and not (landm_t.is_cuda and landm_t.is_contiguous() and tuple(landm_t.shape) == (B, P, 10)
+                                        and landm_t.dtype == torch.float32):
+            raise ValueError("landm_t must be a contiguous CUDA [B,P,10] f32 tensor")
+    else:
+        loc_t = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+        conf_t = torch.empty((B, P), dtype=torch.int64, device=dev)
+        landm_t = torch.empty((B, P, 10), dtype=torch.float32, device=dev) if with_landm else None
+    extra = None
+    bti = bto = bpi = bpo = None
+    if return_match:
+        bti = torch.empty((B, P), dtype=torch.int32, device=dev)
+        bto = torch.empty((B, P), dtype=torch.float32, device=dev)
+        bpi = torch.empty((sumG,), dtype=torch.int32, device=dev)
+        bpo = torch.empty((sumG,), dtype=torch.float32, device=dev)
+        extra = dict(best_truth_idx=bti, best_truth_overlap=bto, best_prior_idx=bpi, best_prior_overlap=bpo)
+    L = _lib.lib()
+    ws = _tensor.workspace(L.jabd_assign_workspace_bytes(B, P, sumG), dev)
+    with torch.cuda.device(dev):
+        _lib.call("jabd_assign", ptr(pri), P, ptr(gt), ptr(offs), B, sumG, float(threshold), v0, v1, int(label_mode),
+                  1 if encode else 0, FLAG_DENSE if dense else 0, ptr(loc_t), ptr(conf_t), ptr(landm_t), ptr(bti), ptr(bto),
+                  ptr(bpi), ptr(bpo), ptr(ws), ws.numel(), _tensor.stream_of(dev))
+    if return_match:
+        return loc_t, conf_t, landm_t, extra
+    return loc_t, conf_t, landm_t
+
+
+def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000,
+           nms_thres=0.4, keep_topk=750):
+    """Fused decode -> class-1 score threshold -> top-k -> NMS -> keep for a batch.
+
+    loc [B,P,4], conf [B,P,2] (softmax probabilities, R/nets/retinaface_eca_nonlocal.py:355-359),
+    landm [B,P,10] or None, priors [P,4].  ``strict``: score > conf_thres (cfg3) else >= (R/utils/utils_bbox.py:266).
+    Returns ``(dets [B,keep_topk,15] zero padded, counts [B] i32, keep_idx [B,keep_topk] i32, -1 padded)`` on the GPU.
+    """
+    dev = _tensor.device_of(loc, conf, priors)
+    loc_d, conf_d, pri = _tensor.to_dev(loc, dev), _tensor.to_dev(conf, dev), _tensor.to_dev(priors, dev)
+    if loc_d.ndim == 2:
+        loc_d, conf_d = loc_d[None], conf_d[None]
+        landm = landm[None] if landm is not None else None
+    landm_d = _tensor.to_dev(landm, dev) if landm is not None else None
+    B, P = int(loc_d.shape[0]), int(loc_d.shape[1])
+    if tuple(loc_d.shape) != (B, P, 4) or tuple(conf_d.shape) != (B, P, 2) or tuple(pri.shape) != (P, 4) or \
+            (landm_d is not None and tuple(landm_d.shape) != (B, P, 10)):
+        raise ValueError("detect: expected loc [B,P,4], conf [B,P,2], landm [B,P,10], priors [P,4]")
+    keep_cap = int(keep_topk) if keep_topk and keep_topk > 0 else P
+    v0, v1 = _tensor.variances_of(variances)
+    dets = torch.empty((B, keep_cap, 15), dtype=torch.float32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    keep_idx = torch.empty((B, keep_cap), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = _tensor.workspace(L.jabd_detect_workspace_bytes(B, P, keep_cap), dev)
+    with torch.cuda.device(dev):
+        _lib.call("jabd_detect", ptr(loc_d), ptr(conf_d), ptr(landm_d), ptr(pri), B, P, v0, v1, float(conf_thres),
+                  THRESH_GT if strict else THRESH_GE, int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), keep_cap,
+                  ptr(dets), ptr(counts), ptr(keep_idx), ptr(ws), ws.numel(), _tensor.stream_of(dev))
+    return dets, counts, keep_idx
+
+
+class HostAssign(object):
+    """End-to-end host-buffer path (``jabd_assign_host``): pinned staging buffers and the device scratch are
+    allocated once for a (B, P, max sumG) shape; each call copies GT in, assigns, copies the targets out."""
+
+    def __init__(self, priors, B, max_sum_g, with_landm=True, device=None):
+        _tensor.require_cuda()
+        self.dev = torch.device(device) if device is not None else _tensor.device_of(priors)
+        self.pri = _tensor.to_dev(priors, self.dev)
+        self.B, self.P, self.cap = int(B), int(self.pri.shape[0]), int(max_sum_g)
+        L = _lib.lib()
+        self.scratch = _tensor.workspace(L.jabd_assign_host_scratch_bytes(self.B, self.P, self.cap, 1 if with_landm else 0), self.dev)
+        self.gt_pin = torch.empty((self.cap, 15), dtype=torch.float32).pin_memory()
+        self.off_pin = torch.empty((self.B + 1,), dtype=torch.int32).pin_memory()
+        self.loc_t = torch.empty((self.B, self.P, 4), dtype=torch.float32).pin_memory()
+        self.conf_t = torch.empty((self.B, self.P), dtype=torch.int64).pin_memory()
+        self.landm_t = torch.empty((self.B, self.P, 10), dtype=torch.float32).pin_memory() if with_landm else None
+
+    def __call__(self, targets, threshold=0.35, variances=(0.1, 0.2), label_mode=0, encode=True, dense=False):
+        off = 0
+        self.off_pin[0] = 0
+        if len(targets) != self.B:
+            raise ValueError("expected %d images" % self.B)
+        for i, t in enumerate(targets):
+            g = int(t.shape[0])
+            if off + g > self.cap:
+                raise ValueError("sumG exceeds the capacity this HostAssign was built for")
+            self.gt_pin[off:off + g].copy_(torch.as_tensor(t))
+            off += g
+            self.off_pin[i + 1] = off
+        v0, v1 = _tensor.variances_of(variances)
+        with torch.cuda.device(self.dev):
+            _lib.call("jabd_assign_host", ptr(self.pri), self.P, ptr(self.gt_pin), ptr(self.off_pin), self.B, float(threshold),
+                      v0, v1, int(label_mode), 1 if encode else 0, FLAG_DENSE if dense else 0, ptr(self.loc_t),
+                      ptr(self.conf_t), ptr(self.landm_t), ptr(self.scratch), self.scratch.numel(),
+                      _tensor.stream_of(self.dev))
+        self.last_h2d = off * 15 * 4 + (self.B + 1) * 4
+        self.last_d2h = self.B * self.P * (16 + 8 + (40 if self.landm_t is not None else 0))
+        return self.loc_t, self.conf_t, self.landm_t
+
+
+def assign_targets_host(priors, targets, **kw):
+    """One-shot host-buffer call; for repeated use build a ``HostAssign`` once."""
+    sum_g = sum(int(t.shape[0]) for t in targets)
+    h = HostAssign(priors, len(targets), max(sum_g, 1), with_landm=kw.pop("with_landm", True))
+    return h(targets, **kw)
+
+
+class HostDetect(object):
+    """End-to-end host-buffer path (``jabd_detect_host``) for a fixed (B, P, keep_cap) shape."""
+
+    def __init__(self, priors, B, keep_topk=750, with_landm=True, device=None):
+        _tensor.require_cuda()
+        self.dev = torch.device(device) if device is not None else _tensor.device_of(priors)
+        self.pri = _tensor.to_dev(priors, self.dev)
+        self.B, self.P = int(B), int(self.pri.shape[0])
+        self.keep_cap = int(keep_topk) if keep_topk and keep_topk > 0 else self.P
+        self.with_landm = with_landm
+        L = _lib.lib()
+        self.scratch = _tensor.workspace(
+            L.jabd_detect_host_scratch_bytes(self.B, self.P, self.keep_cap, 1 if with_landm else 0), self.dev)
+        self.dets = torch.empty((self.B, self.keep_cap, 15), dtype=torch.float32).pin_memory()
+        self.counts = torch.empty((self.B,), dtype=torch.int32).pin_memory()
+        self.keep_idx = torch.empty((self.B, self.keep_cap), dtype=torch.int32).pin_memory()
+
+    def __call__(self, loc, conf, landm, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000,
+                 nms_thres=0.4):
+        for t, shp in ((loc, (self.B, self.P, 4)), (conf, (self.B, self.P, 2))):
+            if t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shp or t.dtype != torch.float32:
+                raise ValueError("HostDetect expects contiguous CPU f32 tensors loc [B,P,4], conf [B,P,2], landm [B,P,10]")
+        v0, v1 = _tensor.variances_of(variances)
+        with torch.cuda.device(self.dev):
+            _lib.call("jabd_detect_host", ptr(loc), ptr(conf), ptr(landm if self.with_landm else None), ptr(self.pri), self.B,
+                      self.P, v0, v1, float(conf_thres), THRESH_GT if strict else THRESH_GE,
+                      int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), self.keep_cap, ptr(self.dets),
+                      ptr(self.counts), ptr(self.keep_idx), ptr(self.scratch), self.scratch.numel(),
+                      _tensor.stream_of(self.dev))
+        self.last_h2d = self.B * self.P * 4 * (4 + 2 + (10 if self.with_landm else 0))
+        self.last_d2h = self.B * (self.keep_cap * (60 + 4) + 4)
+        return self.dets, self.counts, self.keep_idx
+
+
+def detect_host(loc, conf, landm, priors, **kw):
+    h = HostDetect(priors, loc.shape[0], keep_topk=kw.pop("keep_topk", 750), with_landm=landm is not None)
+    return h(loc, conf, landm, **kw)

@@ -1,0 +1,152 @@
+"""CPU-only checks (no CUDA device needed): the C-ABI library builds, loads and exports exactly what
+include/jabd_b200.h declares; host-side argument validation; sharding logic incl. a world-size-2 gloo run.
+No compute entry point is called here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from jabd_b200 import _lib
+    _lib.build()
+    return _lib
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "jabd_b200.h")).read()
+    return sorted(set(re.findall(r"JABD_API[^;(]*?\b(jabd_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    declared = header_symbols()
+    assert len(declared) >= 25
+    L = lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(lib.SIGNATURES) == declared            # the ctypes table mirrors the header one to one
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib.SO_PATH]).decode()
+    exported = sorted(set(re.findall(r" T (jabd_\w+)", out)))
+    assert exported == declared                           # nothing undeclared leaks out either
+    assert L.jabd_version() == 100
+
+
+def test_library_is_sm100a_with_tma(lib):
+    sass = subprocess.check_output(["cuobjdump", "-sass", lib.SO_PATH]).decode()
+    assert "sm_100a" in sass
+    assert "UBLKCP" in sass and "SYNCS" in sass           # cp.async.bulk + mbarrier in the matching kernel
+    assert "REDUX" in sass                                # warp argmax
+
+
+def test_host_side_validation_without_gpu(lib):
+    L = lib.lib()
+    vp = ctypes.c_void_p
+    steps = np.array([8, 16, 32], np.int32)
+    off = np.array([0, 2, 4, 6], np.int32)
+    n = L.jabd_priors_count(vp(steps.ctypes.data), vp(off.ctypes.data), 3, 640, 640)
+    assert n == 16800
+    assert L.jabd_priors_count(vp(steps.ctypes.data), vp(off.ctypes.data), 3, 1024, 1024) == 43008
+    assert L.jabd_priors_count(vp(steps.ctypes.data), vp(off.ctypes.data), 3, 100, 75) == 2 * (13 * 10 + 7 * 5 + 4 * 3)
+    assert L.jabd_priors_count(vp(steps.ctypes.data), vp(off.ctypes.data), 0, 640, 640) == -1
+    assert "n_levels" in lib.last_error()
+    # sizes only: never touches the device
+    w1 = L.jabd_assign_workspace_bytes(32, 16800, 3000)
+    assert w1 >= 32 * 16800 * 8 + 3000 * 24 and w1 % 256 == 0
+    assert L.jabd_assign_host_scratch_bytes(32, 16800, 3000, 1) > w1 + 32 * 16800 * 64
+    assert L.jabd_detect_workspace_bytes(16, 43008, 750) >= 16 * 750 * 20
+    # argument errors are reported before any CUDA call
+    assert L.jabd_assign(None, 16800, None, None, 4, 10, 0.35, 0.1, 0.2, 0, 1, 0, None, None, None, None, None, None, None,
+                         None, 0, None) == -1
+    assert "null" in lib.last_error()
+    assert L.jabd_assign(None, -1, None, None, 4, 10, 0.35, 0.1, 0.2, 0, 1, 0, None, None, None, None, None, None, None,
+                         None, 0, None) == -1
+    buf = np.zeros(64, np.float32)
+    mis = vp(buf.ctypes.data + 4)
+    assert L.jabd_decode(mis, mis, 4, 1, 0.1, 0.2, mis, None) == -2
+    assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 7, 0, 0.3, 0, 4, mis, mis, None, 0, None) == -1
+    with pytest.raises(ValueError):
+        lib.check(-2, "x")
+    with pytest.raises(RuntimeError):
+        lib.check(-4, "x")
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the operators raise instead of computing on the host."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from jabd_b200 import anchors, batched, config, utils_bbox
+    with pytest.raises(RuntimeError):
+        anchors.Anchors(config.cfg_mnet, image_size=(64, 64)).get_anchors()
+    with pytest.raises(RuntimeError):
+        batched.assign_targets(np.zeros((4, 4), np.float32), [np.zeros((1, 15), np.float32)])
+    with pytest.raises(RuntimeError):
+        utils_bbox.decode(np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32), [0.1, 0.2])
+    # and nothing under the product package imports the oracle
+    pkg = os.path.join(ROOT, "jabd-joint-attention-based-detector-for-small-face-detection_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "jabd_oracle" not in src, f
+
+
+def test_shard_bounds():
+    from jabd_b200 import sharding
+    assert sharding.shard_bounds(256, 8) == [32 * i for i in range(9)]
+    assert sharding.shard_bounds(10, 4) == [0, 3, 6, 8, 10]
+    assert sharding.shard_bounds(3, 4) == [0, 1, 2, 3, 3]
+    b = sharding.shard_bounds(6, 2, [300, 1, 1, 1, 1, 296])
+    assert b[0] == 0 and b[-1] == 6 and b == sorted(b)
+    loads = [sum([300, 1, 1, 1, 1, 296][b[i]:b[i + 1]]) for i in range(2)]
+    assert max(loads) <= 304
+    # every item lands in exactly one shard
+    for n, w in ((17, 5), (1, 3), (0, 2), (100, 7)):
+        bb = sharding.shard_bounds(n, w, list(range(1, n + 1)))
+        assert bb[0] == 0 and bb[-1] == n and all(x <= y for x, y in zip(bb, bb[1:]))
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+from jabd_b200 import sharding, synth
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+targets = synth.make_gt_batch(2, 8, (640, 640))
+mine, (lo, hi) = sharding.local_targets(targets)
+# every rank derives the same partition; together the shards cover the batch once
+spans = [None, None]
+dist.all_gather_object(spans, (lo, hi))
+assert spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == 8, spans
+assert [t.shape for t in mine] == [t.shape for t in targets[lo:hi]]
+# fixed-shape all-gather of padded detections (CPU tensors -> gloo path)
+B_local, keep = 4, 6
+dets = torch.full((B_local, keep, 15), float(rank + 1))
+counts = torch.full((B_local,), rank + 3, dtype=torch.int32)
+d, c = sharding.allgather_detections(dets, counts)
+assert d.shape == (8, keep, 15) and (d[:4] == 1).all() and (d[4:] == 2).all()
+assert c.tolist() == [3] * 4 + [4] * 4
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

@@ -1,0 +1,238 @@
+"""GPU parity of the inference side (decode, threshold, top-k, NMS, fused detect) against the CPU oracle and
+the golden vectors recorded from the reference.
+
+bit-exact: landmark decode, top-k index lists, NMS keep lists (order included) on identical box inputs,
+scores.  rtol 1e-5 / atol 1e-6: decoded boxes (exp half; see conftest.RTOL/ATOL).
+The fused pipeline is checked twice: (i) keep lists bit-exact against the oracle fed with the GPU-decoded
+boxes (isolates NMS decisions from the <= 1 ulp exp difference), and (ii) against the
+golden outputs of the real reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import ATOL, RTOL, load_golden
+
+pytestmark = pytest.mark.gpu
+
+VAR = [0.1, 0.2]
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from jabd_b200 import _ops, anchors, batched, box_utils, config, synth, utils_bbox
+    from oracle import oracle as orc
+    return dict(ops=_ops, anchors=anchors, batched=batched, box_utils=box_utils, cfgs=config, synth=synth, ub=utils_bbox,
+                orc=orc)
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_decode_golden_and_oracle(mods):
+    g = load_golden("decode.npz")
+    ub, orc = mods["ub"], mods["orc"]
+    pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(160, 160)).get_anchors()
+    b = ub.decode(cuda(g["loc"]), pri, VAR)
+    np.testing.assert_allclose(b.cpu().numpy(), g["boxes"], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(ub.decode_landm(cuda(g["landm"]), pri, VAR).cpu().numpy(), g["landms"])
+    # how close is the fp64-exp decode to the reference's bits?  (informational, printed with -s)
+    print("decode boxes bit-equal to torch CPU: %.4f" % (b.cpu().numpy() == g["boxes"]).mean())
+    pri640 = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(640, 640)).get_anchors()
+    loc, conf, landm = mods["synth"].make_preds_random(1, 0, pri640.shape[0])
+    np.testing.assert_allclose(ub.decode(loc.cuda(), pri640, VAR).cpu().numpy(), g["boxes640"], rtol=RTOL, atol=ATOL)
+    lm = ub.decode_landm(landm.cuda(), pri640, VAR).cpu().numpy()
+    assert np.array_equal(lm[:1024], g["landms640_head"])
+    assert np.array_equal(lm, orc.decode_landm(landm.numpy(), pri640.cpu().numpy(), VAR))
+    # batched [B,P,*] form equals per-image calls; numpy in -> numpy out
+    locb = torch.stack([loc, loc * 0.5, -loc]).cuda()
+    outb = ub.decode(locb, pri640, VAR)
+    for i in range(3):
+        assert torch.equal(outb[i], ub.decode(locb[i], pri640, VAR))
+    lmb = torch.stack([landm, landm * 2]).cuda()
+    outl = ub.decode_landm(lmb, pri640, VAR)
+    assert torch.equal(outl[1], ub.decode_landm(lmb[1], pri640, VAR))
+    assert isinstance(ub.decode(loc.numpy(), pri640.cpu().numpy(), VAR), np.ndarray)
+    assert np.array_equal(mods["box_utils"].decode(loc.cuda(), pri640, VAR).cpu().numpy(), outb[0].cpu().numpy())
+
+
+def test_topk_segmented(mods):
+    ops = mods["ops"]
+    rng = np.random.default_rng(3)
+    # heavy ties (quantised scores), several segments, K below / above the survivor count
+    s = (rng.integers(0, 50, size=(5, 20000)) / 50.0).astype(np.float32)
+    s[3] = 0.25                       # one segment where every score ties
+    s[4, ::3] = -s[4, ::3]            # negative scores order correctly
+    for k, thr in ((1, None), (100, None), (5000, 0.5), (7000, None), (6144, None), (20000, None), (20000, 0.9)):
+        idx, cnt = ops.topk(cuda(s), k, conf_thres=thr, strict=True)
+        idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+        for r in range(s.shape[0]):
+            sel = np.nonzero(s[r] > np.float32(thr))[0] if thr is not None else np.arange(s.shape[1])
+            order = sel[np.argsort(-s[r][sel].astype(np.float64), kind="stable")][:k]
+            assert cnt[r] == len(order), (k, thr, r)
+            assert np.array_equal(idx[r, :cnt[r]], order), (k, thr, r)
+            assert (idx[r, cnt[r]:] == -1).all()
+    idx, cnt = ops.topk(cuda(s[0]), 10, conf_thres=0.98, strict=False)   # >= keeps the 0.98 bucket
+    ref = np.nonzero(s[0] >= np.float32(0.98))[0][:10]
+    assert np.array_equal(idx.cpu().numpy()[:int(cnt)], ref)
+    idx, cnt = ops.topk(cuda(s[0]), 10, conf_thres=2.0)                   # nothing passes
+    assert int(cnt) == 0 and (idx.cpu().numpy() == -1).all()
+
+
+def test_nms_torchvision_golden(mods):
+    """Keep lists recorded from torchvision.ops.nms (CPU) through the reference's call site."""
+    g = load_golden("nms.npz")
+    ops = mods["ops"]
+    for name in g["names"]:
+        name = str(name)
+        b, s = g[name + "_boxes"], g[name + "_scores"]
+        n = b.shape[0]
+        for thr in (0.3, 0.4, 0.5):
+            ref = g["%s_keep_%d" % (name, int(thr * 100))]
+            keep, cnt = ops.nms_indices(cuda(b), 4, cuda(s), 1, n, 0.0, ops.THRESH_NONE, 0, thr, ops.NMS_TV, n, torch.device("cuda", 0))
+            c = int(cnt.item())
+            assert c == len(ref), (name, thr)
+            assert np.array_equal(keep[:c].cpu().numpy(), ref), (name, thr)
+            assert (keep[c:].cpu().numpy() == -1).all()
+
+
+def test_nms_ssd_golden(mods):
+    g = load_golden("nms.npz")
+    bu, ub = mods["box_utils"], mods["ub"]
+    for name in ("rand500", "dense2000"):
+        b, s = g[name + "_boxes"], g[name + "_scores"]
+        for (ov, tk) in ((0.5, 200), (0.3, 50), (0.45, 5000)):
+            keep, count = bu.nms(cuda(b), cuda(s), ov, tk)
+            assert count == int(g["%s_ssd_%d_%d_count" % (name, int(ov * 100), tk)])
+            assert keep.dtype == torch.int64 and keep.shape[0] == b.shape[0]
+            assert np.array_equal(keep.cpu().numpy(), g["%s_ssd_%d_%d_keep" % (name, int(ov * 100), tk)])
+            keep2, count2 = ub.nms_r(cuda(b), cuda(s), ov, tk)
+            assert count2 == count and torch.equal(keep, keep2)
+    e = bu.nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda())
+    assert isinstance(e, torch.Tensor) and e.numel() == 0      # bare keep on empty input (:397-398)
+
+
+def test_nms_large_uncapped_vs_oracle(mods):
+    """More candidates than one selection round (6144) and more keeps than the shared-memory kept cache (1536):
+    multi-round streaming top-k feeding NMS, kept boxes spilling to the workspace."""
+    ops, orc = mods["ops"], mods["orc"]
+    rng = np.random.default_rng(17)
+    n = 20000
+    c = rng.random((n, 2), dtype=np.float32)
+    wh = 0.004 + 0.02 * rng.random((n, 2), dtype=np.float32)
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    s = rng.random(n, dtype=np.float32)
+    s[::7] = s[3]                                                # ties across rounds
+    for thr in (0.3, 0.5):
+        ref = orc.nms_tv(b, s, thr)
+        assert len(ref) > 1536
+        keep, cnt = ops.nms_indices(cuda(b), 4, cuda(s), 1, n, 0.0, ops.THRESH_NONE, 0, thr, ops.NMS_TV, n, torch.device("cuda", 0))
+        c_ = int(cnt.item())
+        assert c_ == len(ref) and np.array_equal(keep[:c_].cpu().numpy(), ref)
+        # capped keep list == prefix of the uncapped one; pre-NMS top-k == NMS of the k best
+        keep, cnt = ops.nms_indices(cuda(b), 4, cuda(s), 1, n, 0.0, ops.THRESH_NONE, 0, thr, ops.NMS_TV, 100, torch.device("cuda", 0))
+        assert int(cnt.item()) == 100 and np.array_equal(keep.cpu().numpy(), ref[:100])
+        order = orc.argsort_desc(s)[:9000]
+        ref_k = order[orc.nms_tv(b[order], s[order], thr)]
+        keep, cnt = ops.nms_indices(cuda(b), 4, cuda(s), 1, n, 0.0, ops.THRESH_NONE, 9000, thr, ops.NMS_TV, n, torch.device("cuda", 0))
+        c_ = int(cnt.item())
+        assert c_ == len(ref_k) and np.array_equal(keep[:c_].cpu().numpy(), ref_k)
+
+
+def _pipeline_inputs(mods, g, tag, gen):
+    size = (160, 160) if tag == "s160" else (640, 640)
+    img = 1 if tag == "s160" else 2
+    pri = mods["orc"].priors(mods["cfgs"].cfg_mnet, size)
+    key = "%s_%s_" % (tag, gen)
+    gt = torch.from_numpy(g[key + "gt"])
+    if gen == "A":
+        loc, conf, landm = mods["synth"].make_preds_random(3, img, pri.shape[0])
+    else:
+        loc, conf, landm = mods["synth"].make_preds_clustered(3, img, torch.from_numpy(pri), gt, VAR)
+    return pri, loc.numpy(), conf.numpy(), landm.numpy()
+
+
+@pytest.mark.parametrize("tag", ["s160", "s640"])
+@pytest.mark.parametrize("gen", ["A", "B"])
+def test_pipeline_golden(mods, tag, gen):
+    """Drop-in non_max_suppression (>= 0.5 / 0.3, uncapped) and the cfg3 pipeline (> 0.02, top-k, 0.4, keep)
+    against outputs of the real reference."""
+    g = load_golden("pipeline.npz")
+    ub, orc = mods["ub"], mods["orc"]
+    pri, loc, conf, landm = _pipeline_inputs(mods, g, tag, gen)
+    key = "%s_%s_" % (tag, gen)
+    pri_c = cuda(pri)
+    boxes = ub.decode(cuda(loc), pri_c, VAR)
+    lms = ub.decode_landm(cuda(landm), pri_c, VAR)
+    det = torch.cat([boxes, cuda(conf)[:, 1:2], lms], -1)               # R/predict.py:180
+    for ct, nt in ((0.5, 0.3), (0.05, 0.3)):
+        ref = g[key + "nms_%d_%d" % (int(ct * 100), int(nt * 100))]
+        out = ub.non_max_suppression(det, ct, nt)
+        out = np.zeros((0, 15), np.float32) if isinstance(out, list) else out
+        # exact vs the oracle on the same (GPU-decoded) boxes
+        exp = orc.non_max_suppression(det.cpu().numpy(), ct, nt)
+        exp = np.zeros((0, 15), np.float32) if isinstance(exp, list) else exp
+        assert np.array_equal(out, exp)
+        # and vs the real reference
+        assert out.shape == ref.shape and out.dtype == np.float32
+        assert np.array_equal(out[:, 4], ref[:, 4])
+        np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    assert ub.non_max_suppression(det, 1.5, 0.3) == []
+    for (ct, topk, nt, keepk) in ((0.02, 5000, 0.4, 750), (0.02, 200, 0.4, 50)):
+        k2 = key + "pipe_%d_%d_" % (topk, keepk)
+        dets, counts, kidx = mods["batched"].detect(cuda(loc)[None], cuda(conf)[None], cuda(landm)[None], pri_c, VAR,
+                                                    conf_thres=ct, strict=True, pre_nms_topk=topk, nms_thres=nt, keep_topk=keepk)
+        c = int(counts[0].item())
+        e_d, e_i = orc.detect(loc, conf, landm, pri, VAR, ct, True, topk, nt, keepk, boxes_override=boxes.cpu().numpy())
+        assert c == len(e_i) and np.array_equal(kidx[0, :c].cpu().numpy(), e_i)
+        assert np.array_equal(dets[0, :c].cpu().numpy(), e_d)
+        assert (dets[0, c:] == 0).all() and (kidx[0, c:] == -1).all()
+        assert np.array_equal(kidx[0, :c].cpu().numpy(), g[k2 + "idx"])
+        np.testing.assert_allclose(dets[0, :c].cpu().numpy(), g[k2 + "dets"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("gen", ["A", "B"])
+def test_detect_cfg3_batch_vs_oracle(mods, gen):
+    """BASELINE configs[2] at full size: 1024x1024 (43,008 priors), > 0.02, top-5000, IoU 0.4, keep 750."""
+    orc, synth = mods["orc"], mods["synth"]
+    pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(1024, 1024)).get_anchors()
+    P = pri.shape[0]
+    assert P == 43008
+    B = 4
+    locs, confs, lms = [], [], []
+    for i in range(B):
+        if gen == "A":
+            l, c, m = synth.make_preds_random(3, i, P)
+        else:
+            gt = synth.make_gt(3, i, (1024, 1024), count=120)
+            l, c, m = synth.make_preds_clustered(3, i, pri.cpu(), gt, VAR)
+        locs.append(l); confs.append(c); lms.append(m)
+    loc, conf, landm = torch.stack(locs), torch.stack(confs), torch.stack(lms)
+    dets, counts, kidx = mods["batched"].detect(loc.cuda(), conf.cuda(), landm.cuda(), pri, VAR)
+    boxes = mods["ub"].decode(loc.cuda(), pri, VAR).cpu().numpy()
+    pn = pri.cpu().numpy()
+    for i in range(B):
+        e_d, e_i = orc.detect(loc[i].numpy(), conf[i].numpy(), landm[i].numpy(), pn, VAR, 0.02, True, 5000, 0.4, 750,
+                              boxes_override=boxes[i])
+        c = int(counts[i].item())
+        assert c == len(e_i), (gen, i)
+        assert np.array_equal(kidx[i, :c].cpu().numpy(), e_i), (gen, i)
+        assert np.array_equal(dets[i, :c].cpu().numpy(), e_d), (gen, i)
+        # without the box override only the exp half may differ, within tolerance, when the keep list agrees
+        p_d, p_i = orc.detect(loc[i].numpy(), conf[i].numpy(), landm[i].numpy(), pn, VAR, 0.02, True, 5000, 0.4, 750)
+        if np.array_equal(p_i, e_i):
+            np.testing.assert_allclose(e_d, p_d, rtol=RTOL, atol=ATOL)
+    # shard invariance and the host-buffer entry
+    d1, c1, k1 = mods["batched"].detect(loc[2:3].cuda(), conf[2:3].cuda(), landm[2:3].cuda(), pri, VAR)
+    assert torch.equal(d1[0], dets[2]) and torch.equal(k1[0], kidx[2]) and int(c1[0]) == int(counts[2])
+    h = mods["batched"].HostDetect(pri, B)
+    hd, hc, hk = h(loc.contiguous(), conf.contiguous(), landm.contiguous())
+    assert torch.equal(hd, dets.cpu()) and torch.equal(hc, counts.cpu()) and torch.equal(hk, kidx.cpu())
+    # no landmarks, >= threshold, uncapped top-k and keep
+    d2, c2, k2 = mods["batched"].detect(loc[:1].cuda(), conf[:1].cuda(), None, pri, VAR, conf_thres=0.5, strict=False,
+                                        pre_nms_topk=0, nms_thres=0.3, keep_topk=0)
+    e_d, e_i = orc.detect(loc[0].numpy(), conf[0].numpy(), landm[0].numpy(), pn, VAR, 0.5, False, 0, 0.3, 0, boxes_override=boxes[0])
+    c = int(c2[0])
+    assert c == len(e_i) and np.array_equal(k2[0, :c].cpu().numpy(), e_i)
+    assert np.array_equal(d2[0, :c, :5].cpu().numpy(), e_d[:, :5]) and (d2[0, :c, 5:] == 0).all()
