@@ -271,7 +271,7 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_step, "launch_us": us_enc,
                 "note": "80*P + 60*G bytes per image (SURVEY 8d) x 32 images; the kernel writes loc/conf/landm targets once"}
     pairs = P * sum(s["sumG"] for s in sets) / SETS
-    phases = {"stage_gt+match_argmax_us": us_match, "match_encode_us": us_enc,
+    phases = {"prep+match_us": us_match, "match_encode_us": us_enc,
               "match_dense_equiv_tflops": 14.0 * pairs / (us_match * 1e-6) / 1e12,
               "note": "match kernels cull GT against the prior tile's bounding box: dense-equivalent rate of 14 fp32 ops per "
                       "prior x GT pair (SURVEY 8d), not executed flops"}

@@ -60,6 +60,10 @@ JABD_API const char *jabd_last_error(void);
 /* Fills SM count and compute capability of the current device.  Synchronous, host only. */
 JABD_API int jabd_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Test hook: compares the library's shared-reciprocal IEEE division with the compiler's div.rn on n pseudo-random
+ * operand pairs.  out[0] = number of mismatches (out[1] scratch), first_bad[4] = (a, d, got, expected). */
+JABD_API int jabd_selftest_div(uint64_t n, uint64_t seed, unsigned long long *out, float *first_bad, jabd_stream_t stream);
+
 /* ---- P1: prior boxes.  Replaces Anchors.get_anchors / Anchors_eval.get_anchors (R/utils/anchors.py:9-42,
  * :43-79).  steps_host[n_levels]; min_sizes_host[sizes_off_host[n_levels]] grouped per level by
  * sizes_off_host[n_levels+1].  Output [P,4] (cx,cy,w,h), float64 arithmetic rounded once to fp32, optional

@@ -325,3 +325,15 @@ def test_errors_are_loud(mods):
     L = _lib.lib()
     rc = L.jabd_assign_match(pri.data_ptr(), pri.shape[0], pri.data_ptr(), pri.data_ptr(), 1, 1, 0, pri.data_ptr(), 16, None)
     assert rc == -3 and "workspace" in _lib.last_error()
+
+
+def test_shared_reciprocal_division_is_ieee(mods):
+    """fdiv_shared() (one refined reciprocal per divisor) must equal the compiler's div.rn bit for bit:
+    2^30 pseudo-random operand pairs incl. zeros, subnormals, infinities and NaNs in the numerator."""
+    from jabd_b200 import _lib
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    bad = torch.zeros(4, dtype=torch.float32, device="cuda")
+    for seed in (1, 0x9E3779B97F4A7C15):
+        _lib.call("jabd_selftest_div", 1 << 30, seed, out.data_ptr(), bad.data_ptr(), None)
+        torch.cuda.synchronize()
+        assert int(out[0].item()) == 0, "mismatch (a, d, got, expected) = %s" % (bad.cpu().tolist(),)
