@@ -2,56 +2,63 @@
 //
 // Replaces the per-image loop of MultiBoxLoss.forward (R/nets/retinaface_training.py:197-214) and match()
 // (:93-162).  Three launches per batch, all on the caller's stream; nothing is allocated, there is no host
-// sync, no atomic and no memset; the [G,P] IoU matrix is never stored.
+// sync and no memset; the [G,P] IoU matrix is never stored.
 //
-//   assign_prep_kernel  image CTAs: GT rows -> packed 16-byte boxes in the workspace + a per-image "well
-//                       formed" flag; tile CTAs: bounding box, smallest prior area and a sanity flag for
-//                       every 256-prior tile (32 B of metadata per tile).
-//   assign_match_kernel two roles in one launch, chosen by blockIdx.y:
-//     column CTAs       (image, 256-prior tile), one prior per thread: best GT per prior (overlaps.max(0),
-//                       :120).  The image's GT boxes are staged into shared memory by the TMA engine
-//                       (cp.async.bulk + mbarrier, 1024 boxes per copy, double buffered).  Each warp tests 32 GT
-//                       per ballot against the bounding box of its 32 priors and visits only the hits, four
-//                       per step so that their loads and divisions overlap.  GT are visited in ascending
-//                       order and only a strictly larger IoU replaces the best: ties keep the lowest index.
-//     row warps         one warp per GT: best prior per GT (overlaps.max(1), :111).  32 tiles are tested per
-//                       ballot against the GT box; a tile is skipped when it cannot intersect the GT or when
-//                       area_gt / min_prior_area < current best (no prior of it can reach the best); the
-//                       surviving tiles are scanned 8 priors per lane; a REDUX max on the IoU bits and a REDUX
-//                       min on the prior index among the ties give the lowest index of the maximum.
-//   match_encode_kernel one CTA per (image, tile): force-match (:127-130, largest j wins), gather of the
-//                       matched GT row, threshold (:143), encode (:61-84), coalesced stores.
+//   assign_prep_kernel  image CTAs: GT rows -> 32-byte records (box, area, "image well formed" flag) in the
+//                       workspace, the image's row-argmax keys zeroed.  tile CTAs: per 256-prior tile a sanity flag,
+//                       the bounding box of each of its 8 warps' priors, the column-argmax keys of the tile zeroed
+//                       for every image.  one scan CTA: the work list -- every image's GT cut into segments of <= 64
+//                       (image, first GT, count, record offset) -- and the work-queue head.
+//   assign_match_kernel persistent CTAs (4 per SM) pull work items (prior tile, GT segment) from an atomic queue,
+//                       coarse-level tiles first (their large priors intersect most GT and make the longest items).
+//                       One elected thread runs a three-deep software pipeline: queue ticket for item i+3, work-list
+//                       entry for item i+2, and for item i+1 three bulk copies (cp.async.bulk + mbarrier: the GT
+//                       segment, the tile's 256 priors, its warp boxes) into the other half of a double buffer --
+//                       so that no global-memory latency is exposed between items.  Per item each warp tests 32 GT
+//                       per ballot against the bounding box of its 32 priors and visits only the hits, four per step
+//                       so that their loads and divisions overlap (one prior per lane).
+//       column argmax   best GT per prior (overlaps.max(0), :120): in registers over the segment (ascending GT index,
+//                       strict >, so ties keep the lowest index), then one 64-bit atomicMax per prior on the packed key
+//                       (ordered IoU bits << 32 | ~GT index) to combine the segments.
+//       row argmax      best prior per GT (overlaps.max(1), :111): per visited GT a REDUX max over the warp's 32 IoU
+//                       bit patterns; the lane(s) holding it issue a 64-bit atomicMax on the GT's packed key
+//                       (ordered IoU bits << 32 | ~prior index).
+//                       The largest key is the largest IoU and, among equal IoUs, the lowest index -- torch.max's
+//                       first-maximum rule -- so indices match the reference bit for bit.
+//   match_encode_kernel one CTA per (image, tile): unpack the keys, force-match (:127-130, largest j wins), gather
+//                       of the matched GT row, threshold (:143), encode (:61-84), coalesced stores.
 //
 // Why culling is exact: with well-formed inputs (finite coordinates, GT area in [0, 2^40], prior area in
 // [2^-40, 2^40]) every IoU is >= +0 and a pair whose boxes do not intersect has IoU == +0 exactly, which can
-// neither replace a best (strict >, both argmaxes start at value 0 / index 0 like torch.max over zeros) nor tie
-// with a positive one.  JABD_ASSIGN_DENSE disables culling and pruning and evaluates all P*G pairs twice (once per
-// argmax); tests compare the two bit for bit.  Malformed inputs (negative or non-finite areas) select a generic
-// dense path with torch.max's NaN/ordering semantics per warp.
+// neither replace a best (strict >; both argmaxes start at value 0 / index 0 like torch.max over zeros -- a key
+// that is still zero after the launch decodes to exactly that) nor tie with a positive one.  JABD_ASSIGN_DENSE
+// disables culling and evaluates all P*G pairs; tests compare the two bit for bit.  If any prior, or any GT of an
+// image, is malformed (negative or non-finite area) that image takes a generic dense path with torch.max's
+// NaN-wins / first-index semantics.
 #include "common.cuh"
 
 namespace jabd {
 
-constexpr int kTile = 256;    // priors per column CTA, one per thread
-constexpr int kChunk = 1024;  // GT boxes per bulk copy (16 KB), two buffers
-constexpr int kMaxRowCtas = 64; // row-role CTAs per image (8 warps each, one GT per warp per pass)
-constexpr int kWide = 4;      // GT hits processed per step by a column warp
+constexpr int kTile = 256;       // priors per work item, one per thread
+constexpr int kSeg = 64;         // GT per work item (bounds the longest per-warp dependency chain)
+constexpr int kWide = 4;         // GT hits processed per step by a warp
+constexpr int kMatchCtasPerSm = 4;
 
-struct TileMeta {
-    float4 box; // bounding box of the tile's priors (point form)
-    float amin; // smallest prior area of the tile
-    int ok;     // every prior area within [2^-40, 2^40]
+struct __align__(32) GtRec {
+    float4 box;  // x1 y1 x2 y2
+    float area;
+    int img_ok;  // every GT of the image has a finite area in [0, 2^40]
     int pad0, pad1;
 };
 
 struct AssignWorkspace {
-    float4 *gtbox;   // [sumG] x1 y1 x2 y2
-    int *bpi;        // [sumG] best prior per GT
-    float *bpo;      // [sumG] its IoU
-    TileMeta *tiles; // [ceil(P/256)]
-    int *bti;        // [B,P] best GT per prior (before the force-match override)
-    float *bto;      // [B,P] its IoU
-    int *img_ok;     // [B]
+    GtRec *gtrec;               // [sumG]
+    unsigned long long *rowkey; // [sumG] best prior per GT (0 = value +0 at prior 0)
+    unsigned long long *colkey; // [B,P]  best GT per prior before the force-match override (0 = value +0 at GT 0)
+    float4 *wbox;               // [n_tiles*8] bounding box of each warp's 32 priors (point form)
+    int *tile_ok;               // [n_tiles] every prior area of the tile within [2^-40, 2^40]
+    int4 *segs;                 // work list: (image, first GT within the image, count, record offset)
+    int *ctl;                   // [0] number of segments, [1] work-queue head
 };
 
 static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *w, char *base)
@@ -64,33 +71,37 @@ static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *
     };
     const size_t ng = (size_t)(sumG > 0 ? sumG : 1);
     const size_t nt = (size_t)((P + kTile - 1) / kTile) + 1;
-    size_t o_box = take(sizeof(float4) * ng);
-    size_t o_bpi = take(sizeof(int) * ng);
-    size_t o_bpo = take(sizeof(float) * ng);
-    size_t o_tiles = take(sizeof(TileMeta) * nt);
-    size_t o_bti = take(sizeof(int) * (size_t)B * (size_t)P);
-    size_t o_bto = take(sizeof(float) * (size_t)B * (size_t)P);
-    size_t o_ok = take(sizeof(int) * (size_t)(B > 0 ? B : 1));
+    const size_t nseg = (size_t)(B > 0 ? B : 0) + (size_t)(sumG > 0 ? sumG : 0) / kSeg + 1;
+    size_t o_rec = take(sizeof(GtRec) * ng);
+    size_t o_row = take(sizeof(unsigned long long) * ng);
+    size_t o_col = take(sizeof(unsigned long long) * (size_t)B * (size_t)P);
+    size_t o_wbox = take(sizeof(float4) * nt * (kTile / 32));
+    size_t o_tiles = take(sizeof(int) * nt);
+    size_t o_segs = take(sizeof(int4) * nseg);
+    size_t o_ctl = take(sizeof(int) * 4);
     if (w) {
-        w->gtbox = reinterpret_cast<float4 *>(base + o_box);
-        w->bpi = reinterpret_cast<int *>(base + o_bpi);
-        w->bpo = reinterpret_cast<float *>(base + o_bpo);
-        w->tiles = reinterpret_cast<TileMeta *>(base + o_tiles);
-        w->bti = reinterpret_cast<int *>(base + o_bti);
-        w->bto = reinterpret_cast<float *>(base + o_bto);
-        w->img_ok = reinterpret_cast<int *>(base + o_ok);
+        w->gtrec = reinterpret_cast<GtRec *>(base + o_rec);
+        w->rowkey = reinterpret_cast<unsigned long long *>(base + o_row);
+        w->colkey = reinterpret_cast<unsigned long long *>(base + o_col);
+        w->wbox = reinterpret_cast<float4 *>(base + o_wbox);
+        w->tile_ok = reinterpret_cast<int *>(base + o_tiles);
+        w->segs = reinterpret_cast<int4 *>(base + o_segs);
+        w->ctl = reinterpret_cast<int *>(base + o_ctl);
     }
     return off;
 }
 
 // -------------------------------------------------------------------------------------------------------
-// blockIdx.x < B: image role; otherwise tile role.
+// blockIdx.x < B: image role; < B + n_tiles: tile role; == B + n_tiles: scan role.
 __global__ void __launch_bounds__(kTile) assign_prep_kernel(const float *__restrict__ gt, const int *__restrict__ gt_off,
-                                                            const float4 *__restrict__ priors, int P, int B, AssignWorkspace ws)
+                                                            const float4 *__restrict__ priors, int P, int B, int n_tiles,
+                                                            int queue_head, AssignWorkspace ws)
 {
-    __shared__ float red[5][kTile / 32];
+    __shared__ int s_scan[kTile / 32];
     const int tid = threadIdx.x;
-    if ((int)blockIdx.x < B) {
+    const unsigned lane = lane_id();
+    const int warp = tid >> 5;
+    if ((int)blockIdx.x < B) { // ---- image role
         const int b = blockIdx.x;
         const int g0 = gt_off[b];
         const int G = gt_off[b + 1] - g0;
@@ -98,57 +109,84 @@ __global__ void __launch_bounds__(kTile) assign_prep_kernel(const float *__restr
         for (int g = tid; g < G; g += kTile) {
             const float *r = gt + (size_t)(g0 + g) * JABD_GT_ROW;
             const float4 a = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-            ws.gtbox[g0 + g] = a;
             const float aa = box_area(a);
             ok &= (aa >= 0.0f && aa <= 0x1p40f) ? 1 : 0; // false for NaN / inf coordinates too
         }
         ok = __syncthreads_and(ok);
-        if (tid == 0) ws.img_ok[b] = ok;
+        for (int g = tid; g < G; g += kTile) {
+            const float *r = gt + (size_t)(g0 + g) * JABD_GT_ROW;
+            GtRec rec;
+            rec.box = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
+            rec.area = box_area(rec.box);
+            rec.img_ok = ok;
+            rec.pad0 = rec.pad1 = 0;
+            ws.gtrec[g0 + g] = rec;
+            ws.rowkey[g0 + g] = 0ull;
+        }
         return;
     }
     const int t = (int)blockIdx.x - B;
-    const int p = t * kTile + tid;
-    const bool valid = p < P;
-    float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F, amin = CUDART_INF_F;
-    int ok = 1;
-    if (valid) {
-        const float4 pb = to_point_form(__ldg(priors + p));
-        const float area = box_area(pb);
-        x1 = pb.x; y1 = pb.y; x2 = pb.z; y2 = pb.w; amin = area;
-        ok = (area >= 0x1p-40f && area <= 0x1p40f) ? 1 : 0;
-    }
+    if (t < n_tiles) { // ---- tile role
+        const int p = t * kTile + tid;
+        const bool valid = p < P;
+        int ok = 1;
+        float x1 = CUDART_INF_F, y1 = CUDART_INF_F, x2 = -CUDART_INF_F, y2 = -CUDART_INF_F;
+        if (valid) {
+            const float4 pb = to_point_form(__ldg(priors + p));
+            const float area = box_area(pb);
+            ok = (area >= 0x1p-40f && area <= 0x1p40f) ? 1 : 0;
+            x1 = pb.x; y1 = pb.y; x2 = pb.z; y2 = pb.w;
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        x1 = fminf(x1, __shfl_xor_sync(kFull, x1, o));
-        y1 = fminf(y1, __shfl_xor_sync(kFull, y1, o));
-        x2 = fmaxf(x2, __shfl_xor_sync(kFull, x2, o));
-        y2 = fmaxf(y2, __shfl_xor_sync(kFull, y2, o));
-        amin = fminf(amin, __shfl_xor_sync(kFull, amin, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            x1 = fminf(x1, __shfl_xor_sync(kFull, x1, o));
+            y1 = fminf(y1, __shfl_xor_sync(kFull, y1, o));
+            x2 = fmaxf(x2, __shfl_xor_sync(kFull, x2, o));
+            y2 = fmaxf(y2, __shfl_xor_sync(kFull, y2, o));
+        }
+        if (lane == 0) ws.wbox[t * (kTile / 32) + warp] = make_float4(x1, y1, x2, y2);
+        ok = __syncthreads_and(ok);
+        if (tid == 0) ws.tile_ok[t] = ok;
+        if (valid)
+            for (int b = 0; b < B; ++b) ws.colkey[(size_t)b * P + p] = 0ull;
+        return;
     }
-    if ((tid & 31) == 0) {
-        const int w = tid >> 5;
-        red[0][w] = x1; red[1][w] = y1; red[2][w] = x2; red[3][w] = y2; red[4][w] = amin;
-    }
-    ok = __syncthreads_and(ok);
-    if (tid == 0) {
+    // ---- scan role: segment list in image order
+    int running = 0;
+    for (int base = 0; base < B; base += kTile) {
+        const int b = base + tid;
+        int g0 = 0, G = 0;
+        if (b < B) { g0 = gt_off[b]; G = gt_off[b + 1] - g0; }
+        const int c = G > 0 ? (G + kSeg - 1) / kSeg : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < kTile / 32; ++w) {
-            x1 = fminf(x1, red[0][w]); y1 = fminf(y1, red[1][w]);
-            x2 = fmaxf(x2, red[2][w]); y2 = fmaxf(y2, red[3][w]);
-            amin = fminf(amin, red[4][w]);
+            const int v = s_scan[w];
+            if (w < warp) before += v;
+            total += v;
         }
-        TileMeta m;
-        m.box = make_float4(x1, y1, x2, y2);
-        m.amin = amin;
-        m.ok = ok;
-        m.pad0 = m.pad1 = 0;
-        ws.tiles[t] = m;
+        const int first = running + before + incl - c;
+        for (int k = 0; k < c; ++k) {
+            const int c0 = k * kSeg;
+            ws.segs[first + k] = make_int4(b, c0, (G - c0) < kSeg ? (G - c0) : kSeg, g0 + c0);
+        }
+        running += total;
+        __syncthreads();
     }
+    if (tid == 0) { ws.ctl[0] = running; ws.ctl[1] = queue_head; }
 }
 
 // -------------------------------------------------------------------------------------------------------
 // IoU of a well-formed pair (union in [2^-40, 2^42], inter >= 0): the bits of __fdiv_rn(inter, union) unless the
-// intersection is a non-zero value below 2^-60, which sets `slow` instead (the caller then redoes its whole block
+// intersection is a non-zero value below 2^-60, which sets `slow` instead (the caller then redoes its whole step
 // with the generic divide).  Straight-line code: callers unroll several pairs and rely on the compiler to overlap
 // their loads, min/max chains and divisions -- a branch per pair would serialise them.
 __device__ __forceinline__ float iou_wellformed(float4 a, float area_a, float4 b, float area_b, bool &slow)
@@ -161,231 +199,194 @@ __device__ __forceinline__ float iou_wellformed(float4 a, float area_a, float4 b
     return fdiv_fast(inter, uni, rcp_refined(uni));
 }
 
-struct ColSmem {
-    float4 raw[2][kChunk]; // TMA destinations
+// atomicMax on a 64-bit key assembled from two 32-bit halves, predicated (no branch, no return value): RED.MAX.64
+__device__ __forceinline__ void red_max_key(unsigned long long *addr, uint32_t hi, uint32_t lo, bool pred)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b64 k;\n\t"
+        "setp.ne.u32 q, %3, 0;\n\t"
+        "mov.b64 k, {%2, %1};\n\t"
+        "@q red.global.max.u64 [%0], k;\n\t}"
+        :
+        : "l"(addr), "r"(hi), "r"(lo), "r"((uint32_t)pred)
+        : "memory");
+}
+
+struct ItemMeta {
+    int tile;   // < 0: queue drained
+    int image;
+    int c0;     // first GT of the segment within the image
+    int n;      // GT in the segment
+    int rec0;   // offset of the segment in gtrec / rowkey
+    int pad0, pad1, pad2;
+};
+
+struct MatchSmem {
+    GtRec gt[2][kSeg];            // bulk-copy destinations (2 x 2 KB)
+    float4 pri[2][kTile];         //                        (2 x 4 KB)
+    float4 wbox[2][kTile / 32];   //                        (2 x 128 B)
+    ItemMeta meta[2];
     uint64_t mbar[2];
 };
 
-// MODE 0: culled (ballot of 32 GT against the warp's bounding box), MODE 1: dense, MODE 2: dense generic
+// One GT segment against the warp's 32 priors.  MODE 0: culled (ballot of 32 GT against the warp's bounding box),
+// MODE 1: dense, MODE 2: dense with torch.max's NaN / ordering semantics (malformed input).
+//   rowkeys: row-argmax keys of this segment's GT;  p: this lane's prior index;  best/bidx: column argmax over the segment
+//   (bidx relative to the segment).
 template <int MODE>
-__device__ __forceinline__ void column_consume(const float4 *__restrict__ raw, int n, int c0, float4 pb, float area_p, float4 wbox,
-                                               bool valid, float &best, int &bidx, bool &have_best)
+__device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, int n, unsigned long long *rowkeys, float4 pb,
+                                                float area_p, float4 wbox, int p, bool valid, float &best, int &bidx,
+                                                bool &have_best)
 {
     const unsigned lane = lane_id();
+    if (MODE == 2) {
+        for (int j = 0; j < n; ++j) {
+            const float4 a = rec[j].box;
+            const float v = iou_ref(a, rec[j].area, pb, area_p);
+            uint32_t hi = 0, lo = 0;
+            if (valid) {
+                if (!have_best) { best = v; bidx = j; have_best = true; }
+                else if (!(best != best) && ((v != v) || v > best)) { best = v; bidx = j; }
+                hi = ord_of(v);
+                lo = 0xffffffffu - (uint32_t)p;
+            }
+            const uint32_t whi = __reduce_max_sync(kFull, hi);
+            const uint32_t wlo = __reduce_max_sync(kFull, hi == whi ? lo : 0u);
+            if (lane == 0 && (whi | wlo)) atomicMax(rowkeys + j, ((unsigned long long)whi << 32) | wlo);
+        }
+        return;
+    }
+    const uint32_t notp = 0xffffffffu - (uint32_t)p;
     for (int base = 0; base < n; base += 32) {
         const int e = base + (int)lane;
         bool hit = e < n;
         if (MODE == 0 && hit) {
-            const float4 a = raw[e];
+            const float4 a = rec[e].box;
             const float w = fsub(fminf(a.z, wbox.z), fmaxf(a.x, wbox.x));
             const float h = fsub(fminf(a.w, wbox.w), fmaxf(a.y, wbox.y));
             hit = (w > 0.0f) && (h > 0.0f);
         }
         unsigned m = __ballot_sync(kFull, hit);
-        if (MODE != 2) {
-            while (m) {
-                float v[kWide];
-                int j[kWide];
-                bool live[kWide];
-                float4 a[kWide];
+        while (m) {
+            // up to kWide hits per step; a short step repeats its last hit (re-evaluating a GT changes nothing:
+            // strict > for the column, max for the row)
+            int j[kWide];
+            float4 a[kWide];
+            float aa[kWide];
+            float v[kWide];
 #pragma unroll
-                for (int k = 0; k < kWide; ++k) {
-                    j[k] = base + (m ? (__ffs(m) - 1) : 0);
-                    live[k] = m != 0u;
-                    m &= m - 1; // no-op once m == 0
-                    a[k] = raw[j[k]];
-                }
-                bool slow = false;
-#pragma unroll
-                for (int k = 0; k < kWide; ++k) v[k] = iou_wellformed(a[k], box_area(a[k]), pb, area_p, slow);
-                if (slow) { // a sliver intersection below 2^-60 somewhere in this step: generic IEEE divide
-#pragma unroll
-                    for (int k = 0; k < kWide; ++k) v[k] = iou_ref(a[k], box_area(a[k]), pb, area_p);
-                }
-#pragma unroll
-                for (int k = 0; k < kWide; ++k) { // ascending GT index, strict > : ties keep the lowest index
-                    if (live[k] && v[k] > best) { best = v[k]; bidx = c0 + j[k]; } // !live: padding of a short step
-                }
+            for (int k = 0; k < kWide; ++k) {
+                j[k] = (m || k == 0) ? base + __ffs(m) - 1 : j[k > 0 ? k - 1 : 0];
+                m &= m - 1; // no-op once m == 0
+                a[k] = rec[j[k]].box;
+                aa[k] = rec[j[k]].area;
             }
-        } else {
-            while (m) {
-                const int j = base + __ffs(m) - 1;
-                m &= m - 1;
-                const float4 a = raw[j];
-                const float v = iou_ref(a, box_area(a), pb, area_p);
-                if (valid) {
-                    if (!have_best) { best = v; bidx = c0 + j; have_best = true; }
-                    else if (!(best != best) && ((v != v) || v > best)) { best = v; bidx = c0 + j; }
-                }
+            bool slow = false;
+#pragma unroll
+            for (int k = 0; k < kWide; ++k) v[k] = iou_wellformed(a[k], aa[k], pb, area_p, slow);
+            if (slow) { // a sliver intersection below 2^-60 somewhere in this step: generic IEEE divide
+#pragma unroll
+                for (int k = 0; k < kWide; ++k) v[k] = iou_ref(a[k], aa[k], pb, area_p);
+            }
+#pragma unroll
+            for (int k = 0; k < kWide; ++k) {
+                // column argmax: ascending GT index, strict > : ties keep the lowest index
+                if (v[k] > best) { best = v[k]; bidx = j[k]; }
+                // row argmax: the warp's largest IoU for this GT; every lane that holds it (ties are rare) pushes its
+                // own key, the 64-bit max keeps the lowest prior index.  +0 / -0 / lanes past P never push.
+                const uint32_t bits = __float_as_uint(fmaxf(v[k], 0.0f));
+                const uint32_t wmax = __reduce_max_sync(kFull, bits);
+                red_max_key(rowkeys + j[k], bits | 0x80000000u, notp, bits == wmax && bits != 0u);
             }
         }
     }
 }
 
-__device__ __forceinline__ void column_role(const float4 *__restrict__ priors, int P, int b, int tile, int g0, int G,
-                                            const AssignWorkspace &ws, int dense, ColSmem &s)
+__global__ void __launch_bounds__(kTile, kMatchCtasPerSm) assign_match_kernel(const float4 *__restrict__ priors, int P,
+                                                                              AssignWorkspace ws, int dense, int n_tiles)
 {
+    __shared__ __align__(128) MatchSmem s;
     const int tid = threadIdx.x;
-    const unsigned lane = lane_id();
-    const int p = tile * kTile + tid;
-    const bool valid = p < P;
-    // out-of-range threads carry a box that never has a positive intersection
-    float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-    float area_p = 1.0f;
-    if (valid) {
-        pb = to_point_form(__ldg(priors + p));
-        area_p = box_area(pb);
-    }
+    const int warp = tid >> 5;
+    const int n_seg = ws.ctl[0];
+    const long long n_items = (long long)n_seg * n_tiles;
+
+    int all_ok = 1;
+    for (int t = tid; t < n_tiles; t += kTile) all_ok &= ws.tile_ok[t];
     if (tid == 0) { mbar_init(&s.mbar[0], 1); mbar_init(&s.mbar[1], 1); }
-    __syncthreads();
-    const int nchunks = (G + kChunk - 1) / kChunk;
-    if (tid == 0) { // first GT chunk: in flight while the warp bounding boxes are reduced
-        const int n0 = G < kChunk ? G : kChunk;
-        mbar_arrive_expect_tx(&s.mbar[0], (uint32_t)n0 * 16u);
-        bulk_g2s(s.raw[0], ws.gtbox + g0, (uint32_t)n0 * 16u, &s.mbar[0]);
-    }
-    const bool prior_ok = !valid || (area_p >= 0x1p-40f && area_p <= 0x1p40f);
-    float bx1 = valid ? pb.x : CUDART_INF_F, by1 = valid ? pb.y : CUDART_INF_F;
-    float bx2 = valid ? pb.z : -CUDART_INF_F, by2 = valid ? pb.w : -CUDART_INF_F;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        bx1 = fminf(bx1, __shfl_xor_sync(kFull, bx1, o));
-        by1 = fminf(by1, __shfl_xor_sync(kFull, by1, o));
-        bx2 = fmaxf(bx2, __shfl_xor_sync(kFull, bx2, o));
-        by2 = fmaxf(by2, __shfl_xor_sync(kFull, by2, o));
-    }
-    const float4 wbox = make_float4(bx1, by1, bx2, by2);
-    const int mode = (__all_sync(kFull, prior_ok) && ws.img_ok[b]) ? (dense ? 1 : 0) : 2; // per warp
+    all_ok = __syncthreads_and(all_ok);
 
-    float best = 0.0f;
-    int bidx = 0;
-    bool have_best = false;
-    uint32_t ph0 = 0, ph1 = 0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        const int c0 = c * kChunk;
-        const int n = (G - c0) < kChunk ? (G - c0) : kChunk;
-        if (tid == 0 && c + 1 < nchunks) { // the other buffer was released by the barrier that ended step c-1
-            const int nn = (G - c0 - kChunk) < kChunk ? (G - c0 - kChunk) : kChunk;
-            mbar_arrive_expect_tx(&s.mbar[buf ^ 1], (uint32_t)nn * 16u);
-            bulk_g2s(s.raw[buf ^ 1], ws.gtbox + g0 + c0 + kChunk, (uint32_t)nn * 16u, &s.mbar[buf ^ 1]);
+    // ---- producer (thread 0 only): a three-deep pipeline -- queue ticket for item i+2 -> work-list entry for item i+1
+    // -> bulk copies for item i+1 while item i is being consumed
+    long long item1 = 0, item2 = 0;
+    int4 seg1 = make_int4(0, 0, 0, 0);
+    auto issue = [&](int slot, long long item, int4 seg) {
+        ItemMeta m;
+        m.tile = -1; m.image = seg.x; m.c0 = seg.y; m.n = seg.z; m.rec0 = seg.w; m.pad0 = m.pad1 = m.pad2 = 0;
+        if (item < n_items) {
+            const int tile = n_tiles - 1 - (int)(item / n_seg); // coarse pyramid levels (last tiles) first
+            const int np = (P - tile * kTile) < kTile ? (P - tile * kTile) : kTile;
+            m.tile = tile;
+            s.meta[slot] = m;
+            mbar_arrive_expect_tx(&s.mbar[slot], (uint32_t)(seg.z * 32 + np * 16 + (kTile / 32) * 16));
+            bulk_g2s(s.gt[slot], ws.gtrec + seg.w, (uint32_t)seg.z * 32u, &s.mbar[slot]);
+            bulk_g2s(s.pri[slot], priors + (size_t)tile * kTile, (uint32_t)np * 16u, &s.mbar[slot]);
+            bulk_g2s(s.wbox[slot], ws.wbox + (size_t)tile * (kTile / 32), (kTile / 32) * 16u, &s.mbar[slot]);
+        } else {
+            s.meta[slot] = m;
+            mbar_arrive(&s.mbar[slot]);
         }
-        if (buf == 0) { mbar_wait(&s.mbar[0], ph0); ph0 ^= 1u; }
-        else { mbar_wait(&s.mbar[1], ph1); ph1 ^= 1u; }
-        if (mode == 0) column_consume<0>(s.raw[buf], n, c0, pb, area_p, wbox, valid, best, bidx, have_best);
-        else if (mode == 1) column_consume<1>(s.raw[buf], n, c0, pb, area_p, wbox, valid, best, bidx, have_best);
-        else column_consume<2>(s.raw[buf], n, c0, pb, area_p, wbox, valid, best, bidx, have_best);
-        if (nchunks > 1) __syncthreads();
+    };
+    if (tid == 0) {
+        const long long item0 = blockIdx.x;
+        int4 seg0 = make_int4(0, 0, 0, 0);
+        if (item0 < n_items) seg0 = ws.segs[item0 % n_seg];
+        issue(0, item0, seg0);
+        item1 = (long long)blockIdx.x + gridDim.x;
+        if (item1 < n_items) seg1 = ws.segs[item1 % n_seg];
+        item2 = atomicAdd(&ws.ctl[1], 1);
     }
-    if (valid) {
-        ws.bti[(size_t)b * P + p] = bidx;
-        ws.bto[(size_t)b * P + p] = best;
-    }
-}
 
-// One warp per GT: best prior (value, lowest index).
-__device__ __forceinline__ void row_role(const float4 *__restrict__ priors, int P, int b, int r, int g0, int G,
-                                         const AssignWorkspace &ws, int dense, int n_tiles, int row_ctas)
-{
-    const unsigned lane = lane_id();
-    const int warp = threadIdx.x >> 5;
-    if (r * (kTile / 32) + warp >= G) return; // nothing for this warp
-    bool ok = true;
-    for (int t = (int)lane; t < n_tiles; t += 32) ok = ok && (ws.tiles[t].ok != 0);
-    const int mode = (__all_sync(kFull, ok) && ws.img_ok[b]) ? (dense ? 1 : 0) : 2;
-    for (int g = r * (kTile / 32) + warp; g < G; g += row_ctas * (kTile / 32)) {
-        const float4 a = ws.gtbox[g0 + g];
-        const float aa = box_area(a);
-        float best = 0.0f, wbest = 0.0f;
-        uint32_t bp = 0;
-        bool have = false;
-        for (int tbase = 0; tbase < n_tiles; tbase += 32) {
-            const int t = tbase + (int)lane;
-            bool hit = t < n_tiles;
-            float amin = 0.0f;
-            if ((mode == 0) && hit) {
-                const TileMeta tm = ws.tiles[t];
-                amin = tm.amin;
-                const float w = fsub(fminf(a.z, tm.box.z), fmaxf(a.x, tm.box.x));
-                const float h = fsub(fminf(a.w, tm.box.w), fmaxf(a.y, tm.box.y));
-                hit = (w > 0.0f) && (h > 0.0f);
-            }
-            unsigned m = __ballot_sync(kFull, hit);
-            while (m) {
-                const int tl = __ffs(m) - 1;
-                m &= m - 1;
-                if ((mode == 0)) {
-                    // IoU <= area_gt / area_prior: the tile cannot reach the current best (margin covers rounding)
-                    const float am = __shfl_sync(kFull, amin, tl);
-                    if (aa < fmul(fmul(wbest, am), 0.999999f)) continue;
-                }
-                const int pbase = (tbase + tl) * kTile + (int)lane;
-                if (mode != 2) {
-                    float v[kTile / 32];
-                    float4 pr[kTile / 32];
-#pragma unroll
-                    for (int k = 0; k < kTile / 32; ++k) { // all loads first (clamped index: always in range)
-                        const int p = pbase + 32 * k;
-                        pr[k] = __ldg(priors + (p < P ? p : P - 1));
-                    }
-                    bool slow = false;
-#pragma unroll
-                    for (int k = 0; k < kTile / 32; ++k) {
-                        const float4 pb = to_point_form(pr[k]);
-                        v[k] = iou_wellformed(a, aa, pb, box_area(pb), slow);
-                    }
-                    if (slow) {
-#pragma unroll
-                        for (int k = 0; k < kTile / 32; ++k) {
-                            const float4 pb = to_point_form(pr[k]);
-                            v[k] = iou_ref(a, aa, pb, box_area(pb));
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < kTile / 32; ++k) { // ascending prior index per lane, strict >
-                        const int p = pbase + 32 * k;
-                        if (p < P && v[k] > best) { best = v[k]; bp = (uint32_t)p; }
-                    }
-                    wbest = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(best)));
-                } else {
-                    for (int k = 0; k < kTile / 32; ++k) {
-                        const int p = pbase + 32 * k;
-                        if (p < P) {
-                            const float4 pb = to_point_form(__ldg(priors + p));
-                            const float v = iou_ref(a, aa, pb, box_area(pb));
-                            if (!have) { best = v; bp = (uint32_t)p; have = true; }
-                            else if (!(best != best) && ((v != v) || v > best)) { best = v; bp = (uint32_t)p; }
-                        }
-                    }
-                }
-            }
+    uint32_t phases = 0;
+    for (int it = 0;; ++it) {
+        const int slot = it & 1;
+        if (tid == 0) { // slot^1 was released by the barrier that ended the previous iteration
+            issue(slot ^ 1, item1, seg1);
+            item1 = item2;
+            if (item1 < n_items) seg1 = ws.segs[item1 % n_seg];
+            item2 = atomicAdd(&ws.ctl[1], 1);
         }
-        // maximum over lanes, lowest prior index among the ties (torch.max returns the first maximum; NaN wins)
-        const uint32_t u = (mode != 2) ? (__float_as_uint(best) | 0x80000000u) : (have ? ord_of(best) : 0u);
-        const uint32_t wmax = __reduce_max_sync(kFull, u);
-        const uint32_t pmin = __reduce_min_sync(kFull, (u == wmax) ? bp : 0xffffffffu);
-        if (lane == 0) {
-            ws.bpi[g0 + g] = (int)pmin;
-            ws.bpo[g0 + g] = ord_inv(wmax);
+        mbar_wait(&s.mbar[slot], (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+        const ItemMeta meta = s.meta[slot];
+        if (meta.tile < 0) break;
+        const int n = meta.n;
+        const int p = meta.tile * kTile + tid;
+        const bool valid = p < P;
+        // out-of-range threads carry a box that never has a positive intersection
+        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+        float area_p = 1.0f;
+        if (valid) {
+            pb = to_point_form(s.pri[slot][tid]);
+            area_p = box_area(pb);
         }
+        const float4 wbox = s.wbox[slot][warp];
+        const GtRec *rec = s.gt[slot];
+        unsigned long long *rowkeys = ws.rowkey + meta.rec0;
+        const int mode = (all_ok && rec[0].img_ok) ? (dense ? 1 : 0) : 2; // uniform over the image
+        float best = 0.0f;
+        int bidx = 0;
+        bool have_best = false;
+        if (mode == 0) consume_segment<0>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
+        else if (mode == 1) consume_segment<1>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
+        else consume_segment<2>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
+        // combine the segments of the image: max key = largest IoU, then lowest GT index
+        unsigned long long *ck = ws.colkey + (size_t)meta.image * P + p;
+        const uint32_t lo = 0xffffffffu - (uint32_t)(meta.c0 + bidx);
+        if (mode != 2) red_max_key(ck, __float_as_uint(best) | 0x80000000u, lo, valid && best > 0.0f);
+        else if (valid && have_best) atomicMax(ck, make_key(ord_of(best), (uint32_t)(meta.c0 + bidx)));
+        __syncthreads(); // everyone is done with this slot before the producer refills it
     }
-}
-
-// grid: x = image, y = role.  y < row_ctas: row warps; then the prior tiles in REVERSE order.  Launch order is
-// x-fastest, so every image's last tiles -- the large priors of the coarse pyramid levels, which intersect most GT
-// and carry the longest per-warp loops -- start first and the cheap fine-level tiles fill the tail of the launch.
-__global__ void __launch_bounds__(kTile) assign_match_kernel(const float4 *__restrict__ priors, int P,
-                                                             const int *__restrict__ gt_off, AssignWorkspace ws, int dense,
-                                                             int n_tiles)
-{
-    __shared__ __align__(16) ColSmem s;
-    const int b = blockIdx.x;
-    const int g0 = gt_off[b];
-    const int G = gt_off[b + 1] - g0;
-    if (G <= 0) return; // encode kernel writes zeros for this image
-    const int row_ctas = (int)gridDim.y - n_tiles;
-    if ((int)blockIdx.y < row_ctas) row_role(priors, P, b, (int)blockIdx.y, g0, G, ws, dense, n_tiles, row_ctas);
-    else column_role(priors, P, b, (int)gridDim.y - 1 - (int)blockIdx.y, g0, G, ws, dense, s);
 }
 
 // -------------------------------------------------------------------------------------------------------
@@ -424,11 +425,12 @@ __global__ void __launch_bounds__(kTile) match_encode_kernel(EncodeArgs a, Assig
     __syncthreads();
     // force-match: best_truth_idx[best_prior_idx[j]] = j for j ascending -> the largest j wins (:129-130)
     for (int g = tid; g < G; g += kTile) {
-        const uint32_t bp = (uint32_t)ws.bpi[g0 + g];
+        const unsigned long long key = ws.rowkey[g0 + g]; // 0: no positive IoU, i.e. value +0 at prior 0
+        const uint32_t bp = key ? key_idx(key) : 0u;
         if (bp >= (uint32_t)p0 && bp < (uint32_t)(p0 + kTile)) atomicMax(&s_forced[bp - p0], g);
         if (blockIdx.x == 0) {
             if (a.out_bpi) a.out_bpi[g0 + g] = (int)bp;
-            if (a.out_bpo) a.out_bpo[g0 + g] = ws.bpo[g0 + g];
+            if (a.out_bpo) a.out_bpo[g0 + g] = key ? ord_inv(key_ord(key)) : 0.0f;
         }
     }
     __syncthreads();
@@ -441,8 +443,8 @@ __global__ void __launch_bounds__(kTile) match_encode_kernel(EncodeArgs a, Assig
     int idx = 0;
     float ov = 0.0f;
     if (valid && G > 0) {
-        idx = ws.bti[row];
-        ov = ws.bto[row];
+        const unsigned long long ck = ws.colkey[row]; // 0: no positive IoU, i.e. value +0 at GT 0
+        if (ck) { idx = (int)key_idx(ck); ov = ord_inv(key_ord(ck)); }
         const int f = s_forced[tid];
         if (f >= 0) { idx = f; ov = 2.0f; } // :127
         const float *r = a.gt + (size_t)(g0 + idx) * JABD_GT_ROW;
@@ -462,8 +464,8 @@ __global__ void __launch_bounds__(kTile) match_encode_kernel(EncodeArgs a, Assig
                 const float rw = rcp_refined(pr.z), rh = rcp_refined(pr.w), rv = rcp_refined(a.var1);
                 loc.x = fdiv_shared(fsub(fmul(fadd(m.x, m.z), 0.5f), pr.x), dx, rdx);
                 loc.y = fdiv_shared(fsub(fmul(fadd(m.y, m.w), 0.5f), pr.y), dy, rdy);
-                loc.z = fdiv_shared(log_rn(fdiv_shared(fsub(m.z, m.x), pr.z, rw)), a.var1, rv);
-                loc.w = fdiv_shared(log_rn(fdiv_shared(fsub(m.w, m.y), pr.w, rh)), a.var1, rv);
+                loc.z = fdiv_shared(log_f32(fdiv_shared(fsub(m.z, m.x), pr.z, rw)), a.var1, rv);
+                loc.w = fdiv_shared(log_f32(fdiv_shared(fsub(m.w, m.y), pr.w, rh)), a.var1, rv);
             } else {
                 loc = m;
             }
@@ -517,8 +519,8 @@ static int check_assign_common(const float *priors, int64_t P, const float *gt, 
     JABD_REQUIRE(B >= 0 && P >= 0 && sumG >= 0, JABD_EINVAL, "assign: negative size (B=%d P=%lld sumG=%lld)", B,
                  (long long)P, (long long)sumG);
     JABD_REQUIRE(B <= 65535, JABD_EINVAL, "assign: B=%d exceeds 65535 images per call", B);
-    JABD_REQUIRE(P <= (65535ll - kMaxRowCtas) * kTile && sumG < (1ll << 31), JABD_EINVAL,
-                 "assign: at most %lld priors per image and 2^31 GT rows per call", (65535ll - kMaxRowCtas) * kTile);
+    JABD_REQUIRE(P <= 65535ll * kTile && sumG < (1ll << 31), JABD_EINVAL,
+                 "assign: at most %lld priors per image and 2^31 GT rows per call", 65535ll * kTile);
     JABD_REQUIRE((int64_t)B * P < (1ll << 40), JABD_EINVAL, "assign: B*P too large");
     if (B == 0 || P == 0) return JABD_OK;
     JABD_REQUIRE(priors && gt_off && (gt || sumG == 0), JABD_EINVAL, "assign: null input pointer");
@@ -553,15 +555,19 @@ int jabd_assign_match(const float *priors, int64_t P, const float *gt, const int
     AssignWorkspace ws;
     assign_ws_layout(B, P, sumG, &ws, static_cast<char *>(workspace));
     const unsigned n_tiles = (unsigned)((P + kTile - 1) / kTile);
-    assign_prep_kernel<<<(unsigned)B + n_tiles, kTile, 0, st>>>(gt, gt_off, reinterpret_cast<const float4 *>(priors), (int)P, B, ws);
+    int dev = 0, sms = 0;
+    JABD_CUDA(cudaGetDevice(&dev));
+    JABD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // persistent grid: one CTA per resident slot, never more than there can be work items
+    const long long max_items = (long long)n_tiles * ((long long)B + sumG / kSeg);
+    long long grid = (long long)sms * kMatchCtasPerSm;
+    grid = grid < max_items ? grid : max_items;
+    grid = grid < 1 ? 1 : grid;
+    assign_prep_kernel<<<(unsigned)B + n_tiles + 1u, kTile, 0, st>>>(gt, gt_off, reinterpret_cast<const float4 *>(priors), (int)P, B,
+                                                                     (int)n_tiles, (int)(2 * grid), ws);
     JABD_LAUNCH_CHECK("assign_prep_kernel");
-    // row warps: one per GT.  The host only knows the mean GT count, so provision ~2.5x the mean (one pass for
-    // most images); warps beyond an image's G exit at once and larger images take extra passes.
-    long long rows = (5 * sumG / (2 * (long long)B) + kTile / 32 - 1) / (kTile / 32);
-    rows = rows < 4 ? 4 : (rows > kMaxRowCtas ? kMaxRowCtas : rows);
-    const dim3 grid((unsigned)B, n_tiles + (unsigned)rows);
-    assign_match_kernel<<<grid, kTile, 0, st>>>(reinterpret_cast<const float4 *>(priors), (int)P, gt_off, ws,
-                                                (flags & JABD_ASSIGN_DENSE) ? 1 : 0, (int)n_tiles);
+    assign_match_kernel<<<(unsigned)grid, kTile, 0, st>>>(reinterpret_cast<const float4 *>(priors), (int)P, ws,
+                                                          (flags & JABD_ASSIGN_DENSE) ? 1 : 0, (int)n_tiles);
     JABD_LAUNCH_CHECK("assign_match_kernel");
     return JABD_OK;
 }
