@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libjabd_b200.so")
+# JABD_B200_LIB selects another build of the same library (kernel-variant experiments); never a different backend
+SO_PATH = os.environ.get("JABD_B200_LIB") or os.path.join(_HERE, "libjabd_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 c_int, c_i64, c_f32, c_f64, c_sz, c_vp = (ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double,

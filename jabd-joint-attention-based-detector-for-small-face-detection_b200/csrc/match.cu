@@ -40,9 +40,14 @@
 namespace jabd {
 
 constexpr int kTile = 256;       // priors per work item, one per thread
-constexpr int kSeg = 64;         // GT per work item (bounds the longest per-warp dependency chain)
+#ifndef JABD_KSEG
+#define JABD_KSEG 64
+#endif
+constexpr int kSeg = JABD_KSEG;  // GT per work item (bounds the longest per-warp dependency chain)
 constexpr int kWide = 4;         // GT hits processed per step by a warp
 constexpr int kMatchCtasPerSm = 4;
+constexpr int kStages = 4;       // staged work items per CTA: consumer warps may run up to kStages-1 items apart
+constexpr int kMatchThreads = kTile + 32; // 8 consumer warps + 1 producer warp
 
 struct __align__(32) GtRec {
     float4 box;  // x1 y1 x2 y2
@@ -222,11 +227,12 @@ struct ItemMeta {
 };
 
 struct MatchSmem {
-    GtRec gt[2][kSeg];            // bulk-copy destinations (2 x 2 KB)
-    float4 pri[2][kTile];         //                        (2 x 4 KB)
-    float4 wbox[2][kTile / 32];   //                        (2 x 128 B)
-    ItemMeta meta[2];
-    uint64_t mbar[2];
+    GtRec gt[kStages][kSeg];          // bulk-copy destinations (kStages x 2 KB)
+    float4 pri[kStages][kTile];       //                        (kStages x 4 KB)
+    float4 wbox[kStages][kTile / 32]; //                        (kStages x 128 B)
+    ItemMeta meta[kStages];
+    uint64_t full[kStages];           // producer -> consumers: item staged (transaction count)
+    uint64_t empty[kStages];          // consumers -> producer: one arrival per consumer warp
 };
 
 // One GT segment against the warp's 32 priors.  MODE 0: culled (ballot of 32 GT against the warp's bounding box),
@@ -257,6 +263,8 @@ __device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, i
         return;
     }
     const uint32_t notp = 0xffffffffu - (uint32_t)p;
+    char *rowbase = reinterpret_cast<char *>(rowkeys);
+    asm volatile("" : "+l"(rowbase)); // keep the segment's key address materialised: one IMAD.WIDE per push
     for (int base = 0; base < n; base += 32) {
         const int e = base + (int)lane;
         bool hit = e < n;
@@ -296,14 +304,16 @@ __device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, i
                 // own key, the 64-bit max keeps the lowest prior index.  +0 / -0 / lanes past P never push.
                 const uint32_t bits = __float_as_uint(fmaxf(v[k], 0.0f));
                 const uint32_t wmax = __reduce_max_sync(kFull, bits);
-                red_max_key(rowkeys + j[k], bits | 0x80000000u, notp, bits == wmax && bits != 0u);
+                red_max_key(reinterpret_cast<unsigned long long *>(rowbase + ((unsigned)j[k] << 3)), bits | 0x80000000u, notp,
+                            bits == wmax && bits != 0u);
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(kTile, kMatchCtasPerSm) assign_match_kernel(const float4 *__restrict__ priors, int P,
-                                                                              AssignWorkspace ws, int dense, int n_tiles)
+__global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_kernel(const float4 *__restrict__ priors, int P,
+                                                                                      AssignWorkspace ws, int dense,
+                                                                                      int n_tiles)
 {
     __shared__ __align__(128) MatchSmem s;
     const int tid = threadIdx.x;
@@ -312,52 +322,47 @@ __global__ void __launch_bounds__(kTile, kMatchCtasPerSm) assign_match_kernel(co
     const long long n_items = (long long)n_seg * n_tiles;
 
     int all_ok = 1;
-    for (int t = tid; t < n_tiles; t += kTile) all_ok &= ws.tile_ok[t];
-    if (tid == 0) { mbar_init(&s.mbar[0], 1); mbar_init(&s.mbar[1], 1); }
+    for (int t = tid; t < n_tiles; t += kMatchThreads) all_ok &= ws.tile_ok[t];
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], kTile / 32); }
+    }
     all_ok = __syncthreads_and(all_ok);
 
-    // ---- producer (thread 0 only): a three-deep pipeline -- queue ticket for item i+2 -> work-list entry for item i+1
-    // -> bulk copies for item i+1 while item i is being consumed
-    long long item1 = 0, item2 = 0;
-    int4 seg1 = make_int4(0, 0, 0, 0);
-    auto issue = [&](int slot, long long item, int4 seg) {
-        ItemMeta m;
-        m.tile = -1; m.image = seg.x; m.c0 = seg.y; m.n = seg.z; m.rec0 = seg.w; m.pad0 = m.pad1 = m.pad2 = 0;
-        if (item < n_items) {
+    if (warp == kTile / 32) {
+        // ---- producer warp (one lane): queue ticket for item k+1 in flight while item k is resolved and staged
+        if (tid != kTile) return;
+        long long item = blockIdx.x;                      // the first item is static, the rest come from the queue
+        long long next = atomicAdd(&ws.ctl[1], 1);
+        for (int k = 0;; ++k) {
+            const int slot = k % kStages;
+            if (k >= kStages) mbar_wait(&s.empty[slot], (uint32_t)((k / kStages - 1) & 1));
+            ItemMeta m;
+            m.tile = -1; m.image = m.c0 = m.n = m.rec0 = m.pad0 = m.pad1 = m.pad2 = 0;
+            if (item >= n_items) { // queue drained: publish the sentinel and stop
+                s.meta[slot] = m;
+                mbar_arrive(&s.full[slot]);
+                return;
+            }
+            const int4 seg = ws.segs[item % n_seg];
             const int tile = n_tiles - 1 - (int)(item / n_seg); // coarse pyramid levels (last tiles) first
             const int np = (P - tile * kTile) < kTile ? (P - tile * kTile) : kTile;
-            m.tile = tile;
+            m.tile = tile; m.image = seg.x; m.c0 = seg.y; m.n = seg.z; m.rec0 = seg.w;
             s.meta[slot] = m;
-            mbar_arrive_expect_tx(&s.mbar[slot], (uint32_t)(seg.z * 32 + np * 16 + (kTile / 32) * 16));
-            bulk_g2s(s.gt[slot], ws.gtrec + seg.w, (uint32_t)seg.z * 32u, &s.mbar[slot]);
-            bulk_g2s(s.pri[slot], priors + (size_t)tile * kTile, (uint32_t)np * 16u, &s.mbar[slot]);
-            bulk_g2s(s.wbox[slot], ws.wbox + (size_t)tile * (kTile / 32), (kTile / 32) * 16u, &s.mbar[slot]);
-        } else {
-            s.meta[slot] = m;
-            mbar_arrive(&s.mbar[slot]);
+            mbar_arrive_expect_tx(&s.full[slot], (uint32_t)(seg.z * 32 + np * 16 + (kTile / 32) * 16));
+            bulk_g2s(s.gt[slot], ws.gtrec + seg.w, (uint32_t)seg.z * 32u, &s.full[slot]);
+            bulk_g2s(s.pri[slot], priors + (size_t)tile * kTile, (uint32_t)np * 16u, &s.full[slot]);
+            bulk_g2s(s.wbox[slot], ws.wbox + (size_t)tile * (kTile / 32), (kTile / 32) * 16u, &s.full[slot]);
+            item = next;
+            next = atomicAdd(&ws.ctl[1], 1);
         }
-    };
-    if (tid == 0) {
-        const long long item0 = blockIdx.x;
-        int4 seg0 = make_int4(0, 0, 0, 0);
-        if (item0 < n_items) seg0 = ws.segs[item0 % n_seg];
-        issue(0, item0, seg0);
-        item1 = (long long)blockIdx.x + gridDim.x;
-        if (item1 < n_items) seg1 = ws.segs[item1 % n_seg];
-        item2 = atomicAdd(&ws.ctl[1], 1);
     }
 
-    uint32_t phases = 0;
-    for (int it = 0;; ++it) {
-        const int slot = it & 1;
-        if (tid == 0) { // slot^1 was released by the barrier that ended the previous iteration
-            issue(slot ^ 1, item1, seg1);
-            item1 = item2;
-            if (item1 < n_items) seg1 = ws.segs[item1 % n_seg];
-            item2 = atomicAdd(&ws.ctl[1], 1);
-        }
-        mbar_wait(&s.mbar[slot], (phases >> slot) & 1u);
-        phases ^= 1u << slot;
+    // ---- consumer warps: no CTA-wide barrier; a warp releases a stage as soon as it is done with it
+    const unsigned lane = lane_id();
+    for (int k = 0;; ++k) {
+        const int slot = k % kStages;
+        mbar_wait(&s.full[slot], (uint32_t)((k / kStages) & 1));
         const ItemMeta meta = s.meta[slot];
         if (meta.tile < 0) break;
         const int n = meta.n;
@@ -380,12 +385,13 @@ __global__ void __launch_bounds__(kTile, kMatchCtasPerSm) assign_match_kernel(co
         if (mode == 0) consume_segment<0>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
         else if (mode == 1) consume_segment<1>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
         else consume_segment<2>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[slot]); // this warp no longer reads the stage
         // combine the segments of the image: max key = largest IoU, then lowest GT index
         unsigned long long *ck = ws.colkey + (size_t)meta.image * P + p;
         const uint32_t lo = 0xffffffffu - (uint32_t)(meta.c0 + bidx);
         if (mode != 2) red_max_key(ck, __float_as_uint(best) | 0x80000000u, lo, valid && best > 0.0f);
         else if (valid && have_best) atomicMax(ck, make_key(ord_of(best), (uint32_t)(meta.c0 + bidx)));
-        __syncthreads(); // everyone is done with this slot before the producer refills it
     }
 }
 
@@ -421,6 +427,13 @@ __global__ void __launch_bounds__(kTile) match_encode_kernel(EncodeArgs a, Assig
     const int G = a.gt_off[b + 1] - g0;
     const size_t row = (size_t)b * P + p;
 
+    // issued before the barriers so that their latency overlaps the force-match scan
+    unsigned long long ck = 0ull; // 0: no positive IoU, i.e. value +0 at GT 0
+    float4 pr = make_float4(0.f, 0.f, 1.f, 1.f);
+    if (valid) {
+        ck = ws.colkey[row];
+        pr = __ldg(a.priors + p);
+    }
     s_forced[tid] = -1;
     __syncthreads();
     // force-match: best_truth_idx[best_prior_idx[j]] = j for j ascending -> the largest j wins (:129-130)
@@ -443,47 +456,52 @@ __global__ void __launch_bounds__(kTile) match_encode_kernel(EncodeArgs a, Assig
     int idx = 0;
     float ov = 0.0f;
     if (valid && G > 0) {
-        const unsigned long long ck = ws.colkey[row]; // 0: no positive IoU, i.e. value +0 at GT 0
         if (ck) { idx = (int)key_idx(ck); ov = ord_inv(key_ord(ck)); }
         const int f = s_forced[tid];
         if (f >= 0) { idx = f; ov = 2.0f; } // :127
         const float *r = a.gt + (size_t)(g0 + idx) * JABD_GT_ROW;
         const float4 m = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-        const float4 pr = __ldg(a.priors + p);
         float c = __ldg(r + 14);
         if (a.label_mode) c = fadd(c, 1.0f);       // R/utils/box_utils.py:315
         if (ov < a.threshold) c = 0.0f;            // :143
         conf = (long long)c;                       // float -> int64 store truncates
         // 16 IEEE divisions per prior share 5 divisors: var0*w, var0*h (centre + 10 landmark coordinates), w, h
-        // (size ratio) and var1 -- one refined reciprocal each, see fdiv_shared().
+        // (size ratio) and var1 -- one refined reciprocal each (fdiv_fast).  The fast quotient equals div.rn when
+        // divisor and numerator magnitudes lie in [2^-60, 2^60]; one flag collects that for all of them (an exactly
+        // zero numerator counts as out of range) and the rare thread that fails redoes its row with the generic divide.
         const float dx = fmul(a.var0, pr.z), dy = fmul(a.var0, pr.w);
-        const bool safe = divisor_safe(dx) && divisor_safe(dy) && divisor_safe(pr.z) && divisor_safe(pr.w) && divisor_safe(a.var1);
-        if (safe) {
-            const float rdx = rcp_refined(dx), rdy = rcp_refined(dy);
-            if (a.encode_mode) {
-                const float rw = rcp_refined(pr.z), rh = rcp_refined(pr.w), rv = rcp_refined(a.var1);
-                loc.x = fdiv_shared(fsub(fmul(fadd(m.x, m.z), 0.5f), pr.x), dx, rdx);
-                loc.y = fdiv_shared(fsub(fmul(fadd(m.y, m.w), 0.5f), pr.y), dy, rdy);
-                loc.z = fdiv_shared(log_f32(fdiv_shared(fsub(m.z, m.x), pr.z, rw)), a.var1, rv);
-                loc.w = fdiv_shared(log_f32(fdiv_shared(fsub(m.w, m.y), pr.w, rh)), a.var1, rv);
-            } else {
-                loc = m;
-            }
-            if (a.landm_t) {
+        bool fast = mag_safe(dx) && mag_safe(dy) && mag_safe(pr.z) && mag_safe(pr.w) && mag_safe(a.var1);
+        const float rdx = rcp_refined(dx), rdy = rcp_refined(dy);
+        const float ncx = fsub(fmul(fadd(m.x, m.z), 0.5f), pr.x), ncy = fsub(fmul(fadd(m.y, m.w), 0.5f), pr.y);
+        float nl[10];
+        if (a.landm_t) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    lm[2 * k] = fdiv_shared(fsub(__ldg(r + 4 + 2 * k), pr.x), dx, rdx);
-                    lm[2 * k + 1] = fdiv_shared(fsub(__ldg(r + 5 + 2 * k), pr.y), dy, rdy);
-                }
+            for (int k = 0; k < 5; ++k) {
+                nl[2 * k] = fsub(__ldg(r + 4 + 2 * k), pr.x);
+                nl[2 * k + 1] = fsub(__ldg(r + 5 + 2 * k), pr.y);
+                fast = fast && mag_safe(nl[2 * k]) && mag_safe(nl[2 * k + 1]);
+                lm[2 * k] = fdiv_fast(nl[2 * k], dx, rdx);
+                lm[2 * k + 1] = fdiv_fast(nl[2 * k + 1], dy, rdy);
             }
+        }
+        if (a.encode_mode) {
+            const float rw = rcp_refined(pr.z), rh = rcp_refined(pr.w), rv = rcp_refined(a.var1);
+            const float nw = fsub(m.z, m.x), nh = fsub(m.w, m.y);
+            fast = fast && mag_safe(ncx) && mag_safe(ncy) && mag_safe(nw) && mag_safe(nh);
+            loc.x = fdiv_fast(ncx, dx, rdx);
+            loc.y = fdiv_fast(ncy, dy, rdy);
+            const float lw = log_f32(fdiv_fast(nw, pr.z, rw)), lh = log_f32(fdiv_fast(nh, pr.w, rh));
+            fast = fast && mag_safe(lw) && mag_safe(lh);
+            loc.z = fdiv_fast(lw, a.var1, rv);
+            loc.w = fdiv_fast(lh, a.var1, rv);
         } else {
+            loc = m;
+        }
+        if (!fast) {
             loc = a.encode_mode ? encode_box(m, pr, a.var0, a.var1) : m;
             if (a.landm_t) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    lm[2 * k] = fdiv(fsub(__ldg(r + 4 + 2 * k), pr.x), dx);
-                    lm[2 * k + 1] = fdiv(fsub(__ldg(r + 5 + 2 * k), pr.y), dy);
-                }
+                for (int k = 0; k < 10; ++k) lm[k] = fdiv(nl[k], (k & 1) ? dy : dx);
             }
         }
     }
@@ -501,11 +519,17 @@ __global__ void __launch_bounds__(kTile) match_encode_kernel(EncodeArgs a, Assig
         float *dst = a.landm_t + ((size_t)b * P + p0) * 10;
         const int nf = n_valid * 10;
         if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-            const int n4 = nf >> 2;
             float4 *d4 = reinterpret_cast<float4 *>(dst);
             const float4 *s4 = reinterpret_cast<const float4 *>(s_lm);
-            for (int i = tid; i < n4; i += kTile) d4[i] = s4[i];
-            for (int i = (n4 << 2) + tid; i < nf; i += kTile) dst[i] = s_lm[i];
+            if (n_valid == kTile) { // full tile: 640 vectors, 2.5 per thread
+                d4[tid] = s4[tid];
+                d4[tid + kTile] = s4[tid + kTile];
+                if (tid < kTile / 2) d4[tid + 2 * kTile] = s4[tid + 2 * kTile];
+            } else {
+                const int n4 = nf >> 2;
+                for (int i = tid; i < n4; i += kTile) d4[i] = s4[i];
+                for (int i = (n4 << 2) + tid; i < nf; i += kTile) dst[i] = s_lm[i];
+            }
         } else {
             for (int i = tid; i < nf; i += kTile) dst[i] = s_lm[i];
         }
@@ -564,9 +588,9 @@ int jabd_assign_match(const float *priors, int64_t P, const float *gt, const int
     grid = grid < max_items ? grid : max_items;
     grid = grid < 1 ? 1 : grid;
     assign_prep_kernel<<<(unsigned)B + n_tiles + 1u, kTile, 0, st>>>(gt, gt_off, reinterpret_cast<const float4 *>(priors), (int)P, B,
-                                                                     (int)n_tiles, (int)(2 * grid), ws);
+                                                                     (int)n_tiles, (int)grid, ws);
     JABD_LAUNCH_CHECK("assign_prep_kernel");
-    assign_match_kernel<<<(unsigned)grid, kTile, 0, st>>>(reinterpret_cast<const float4 *>(priors), (int)P, ws,
+    assign_match_kernel<<<(unsigned)grid, kMatchThreads, 0, st>>>(reinterpret_cast<const float4 *>(priors), (int)P, ws,
                                                           (flags & JABD_ASSIGN_DENSE) ? 1 : 0, (int)n_tiles);
     JABD_LAUNCH_CHECK("assign_match_kernel");
     return JABD_OK;
