@@ -251,42 +251,83 @@ def main():
     windows.append(win)
 
     # ---- per-kernel phases (CUDA events on the launching stream, same rotating buffers)
-    n_ph = min(max(K, 200), 2000)
-    for k in range(10):
-        phase_match(sets[k % SETS]); phase_encode(sets[k % SETS])
-    ms_match, _ = timed_loop(lambda k: phase_match(sets[k % SETS]), n_ph)
-    ms_enc, _ = timed_loop(lambda k: phase_encode(sets[k % SETS]), n_ph)
-    us_match, us_enc = ms_match / n_ph * 1e3, ms_enc / n_ph * 1e3
+    # One CUDA graph per phase holding that phase for all SETS buffer sets back to back, so that the host's launch
+    # rate never limits a 5-15 us kernel: time per launch = graph time / SETS.
+    n_ph = min(max(K // SETS, 25), 250)
+
+    def phase_graph(fn):
+        for s_ in sets:
+            fn(s_)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for s_ in sets:
+                fn(s_)
+        return g
+
+    g_prep = phase_graph(lambda s_: phase_match(s_, 2))        # JABD_ASSIGN_PREP_ONLY
+    g_pm = phase_graph(lambda s_: phase_match(s_))             # prep + match
+    g_enc = phase_graph(phase_encode)
+    for g in (g_prep, g_pm, g_enc):
+        g.replay()
+    ms_prep, _ = timed_loop(lambda k: g_prep.replay(), n_ph)
+    ms_match, _ = timed_loop(lambda k: g_pm.replay(), n_ph)
+    ms_enc, _ = timed_loop(lambda k: g_enc.replay(), n_ph)
+    us_prep, us_pm, us_enc = (x / (n_ph * SETS) * 1e3 for x in (ms_prep, ms_match, ms_enc))
+    us_match = max(us_pm - us_prep, 1e-3)
     hbm_peak, peak_src = peaks()
-    bytes_step = BATCH * (80.0 * P) + 60.0 * sum(s["sumG"] for s in sets) / SETS     # 80P + 60G per image
-    enc_gbs = bytes_step / (us_enc * 1e-6) / 1e9
-    traffic = None
+    sum_g = sum(s["sumG"] for s in sets) / SETS
+    pairs = float(P) * sum_g                                   # prior x GT pairs per launch
+    flops_launch = 14.0 * pairs                                # 14 fp32 ops per pair, no FMA
+    bytes_step = BATCH * (80.0 * P) + 60.0 * sum_g             # 80P + 60G per image
+
+    # measured FP32 (non-FMA) peak: dependency-free FMUL/FADD chains on every SM, same clocks as the run
+    sms = ctypes.c_int(0)
+    _lib.call("jabd_device_info", ctypes.byref(sms), None, None)
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    probe_ctas, probe_iters = sms.value * 16, 4096
+    for _ in range(3):
+        _lib.call("jabd_fp32_probe", probe_ctas, probe_iters, ptr(sink), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    ms_probe, _ = timed_loop(lambda k: _lib.call("jabd_fp32_probe", probe_ctas, probe_iters, ptr(sink),
+                                                 ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), 20)
+    fp32_peak = probe_ctas * 256 * 32.0 * probe_iters / (ms_probe / 20 * 1e-3) / 1e12      # Tops/s
+    fp32_nominal = sms.value * 128 * 1.965e9 / 1e12
+
+    traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("match_encode_kernel_bytes_per_launch")
+            traffic = json.load(f)
     except Exception:
         pass
-    roofline = {"kernel": "match_encode_kernel", "bound": "hbm", "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": enc_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_step, "launch_us": us_enc,
-                "note": "80*P + 60*G bytes per image (SURVEY 8d) x 32 images; the kernel writes loc/conf/landm targets once"}
-    pairs = P * sum(s["sumG"] for s in sets) / SETS
-    phases = {"prep+match_us": us_match, "match_encode_us": us_enc,
-              "match_dense_equiv_tflops": 14.0 * pairs / (us_match * 1e-6) / 1e12,
-              "note": "match kernels cull GT against the prior tile's bounding box: dense-equivalent rate of 14 fp32 ops per "
-                      "prior x GT pair (SURVEY 8d), not executed flops"}
+    match_tflops = flops_launch / (us_match * 1e-6) / 1e12
+    enc_gbs = bytes_step / (us_enc * 1e-6) / 1e9
+    # dominant kernel of the step = assign_match_kernel (FP32-pipe bound: no contraction, ~0.3 MB of DRAM reads)
+    roofline = {"kernel": "assign_match_kernel", "bound": "fp32", "achieved": match_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": match_tflops / fp32_peak, "traffic": traffic.get("assign_match_kernel_bytes_per_launch"),
+                "peak_source": "measured in this run: jabd_fp32_probe (FMUL+FADD chains, no FMA) on %d SMs; nominal %d x 128 lanes x "
+                               "1.965 GHz = %.1f" % (sms.value, sms.value, fp32_nominal),
+                "algorithmic_flops_per_launch": flops_launch, "launch_us": us_match,
+                "launch_us_how": "CUDA events around graphs of %d launches: (prep+match) - (prep alone), %d replays each" % (SETS, n_ph),
+                "note": "achieved = 14 fp32 ops x P x sum(G) (dense-equivalent, SURVEY 8d) / kernel time; the kernel culls GT "
+                        "against each warp's prior bounding box, so executed flops are lower than this (see phases.match_dense_*)"}
+    roofline_encode = {"kernel": "match_encode_kernel", "bound": "hbm", "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": enc_gbs / hbm_peak, "traffic": traffic.get("match_encode_kernel_bytes_per_launch"),
+                       "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_step, "launch_us": us_enc,
+                       "note": "80*P + 60*G bytes per image (SURVEY 8d) x 32 images; loc/conf/landm targets written once"}
+    phases = {"prep_us": us_prep, "match_us": us_match, "match_encode_us": us_enc,
+              "match_dense_equiv_tflops": match_tflops, "fp32_peak_measured_tops": fp32_peak, "fp32_peak_nominal_tops": fp32_nominal}
 
     extras = {}
     if not args.no_extras:
-        # dense (no culling) matching: every one of the P*G pairs evaluated -> fp32-pipe figure
-        for k in range(5):
-            phase_match(sets[k % SETS], 1)
-        n_d = min(n_ph, 300)
-        ms_dense, _ = timed_loop(lambda k: phase_match(sets[k % SETS], 1), n_d)
-        us_dense = ms_dense / n_d * 1e3
+        # dense (no culling) matching: every one of the P*G pairs evaluated once -> executed-flops figure
+        g_dense = phase_graph(lambda s_: phase_match(s_, 1))
+        g_dense.replay()
+        n_d = min(n_ph, 40)
+        ms_dense, _ = timed_loop(lambda k: g_dense.replay(), n_d)
+        us_dense = max(ms_dense / (n_d * SETS) * 1e3 - us_prep, 1e-3)
         phases["match_dense_us"] = us_dense
-        phases["match_dense_tflops"] = 14.0 * pairs / (us_dense * 1e-6) / 1e12
-        phases["match_dense_frac_of_fp32_nominal_37.2T"] = phases["match_dense_tflops"] / 37.2
+        phases["match_dense_tflops"] = flops_launch / (us_dense * 1e-6) / 1e12
+        phases["match_dense_frac_of_fp32_measured"] = phases["match_dense_tflops"] / fp32_peak
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region
     host = batched.HostAssign(pri, BATCH, max(s["sumG"] for s in sets))
@@ -401,7 +442,7 @@ def main():
                    "global_batch": world * BATCH, "image": list(IMAGE), "priors": P, "parallelism": "image-sharded x%d, no collective" % world,
                    "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2), one CUDA graph each"
                          % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "cpu_baseline": cpu, "phases": phases,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "phases": phases,
         "detect": detect_info,
     }
     print(json.dumps(line))

@@ -54,6 +54,7 @@ enum {
  *                                                             R/utils/box_utils.py:229-273)         */
 /* flags for jabd_assign */
 #define JABD_ASSIGN_DENSE 1 /* evaluate every prior x GT pair (no spatial culling); same results */
+#define JABD_ASSIGN_PREP_ONLY 2 /* jabd_assign_match only: launch the staging kernel alone (per-kernel timing) */
 
 JABD_API int jabd_version(void);
 JABD_API const char *jabd_last_error(void);
@@ -63,6 +64,11 @@ JABD_API int jabd_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* Test hook: compares the library's shared-reciprocal IEEE division with the compiler's div.rn on n pseudo-random
  * operand pairs.  out[0] = number of mismatches (out[1] scratch), first_bad[4] = (a, d, got, expected). */
 JABD_API int jabd_selftest_div(uint64_t n, uint64_t seed, unsigned long long *out, float *first_bad, jabd_stream_t stream);
+
+/* Bench hook: dependency-free FMUL/FADD chains (no FMA, no memory traffic) on `ctas` CTAs of 256 threads;
+ * ctas * 256 * 32 * iters fp32 operations.  The caller times it: this is the measured FP32-pipe peak that the
+ * matching kernel's roofline is reported against. */
+JABD_API int jabd_fp32_probe(int ctas, int iters, float *sink_dev, jabd_stream_t stream);
 
 /* ---- P1: prior boxes.  Replaces Anchors.get_anchors / Anchors_eval.get_anchors (R/utils/anchors.py:9-42,
  * :43-79).  steps_host[n_levels]; min_sizes_host[sizes_off_host[n_levels]] grouped per level by

@@ -56,9 +56,38 @@ __global__ void __launch_bounds__(256) selftest_div_kernel(unsigned long long n,
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// ---- FP32-pipe throughput probe: the roofline denominator of the matching kernel ----------------------------
+// 16 independent chains per thread, alternating FMUL and FADD (never fused: --fmad=false and _rn intrinsics), i.e. the
+// instruction mix of the IoU arithmetic without any memory traffic.  2 * 16 * iters operations per thread.
+__global__ void __launch_bounds__(256) fp32_probe_kernel(int iters, float seed, float *sink)
+{
+    float x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = seed + (float)(threadIdx.x + k);
+    const float m = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = __fadd_rn(__fmul_rn(x[k], m), c);
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += x[k];
+    if (acc == 123.456f) sink[0] = acc; // never true; keeps the chains alive
+}
+
 } // namespace jabd
 
 extern "C" {
+
+/* Launches the FP32 probe on `ctas` CTAs of 256 threads; the caller times it.  Operations executed:
+ * ctas * 256 * 32 * iters (half FMUL, half FADD). */
+int jabd_fp32_probe(int ctas, int iters, float *sink_dev, jabd_stream_t stream)
+{
+    JABD_REQUIRE(ctas > 0 && iters > 0 && sink_dev, JABD_EINVAL, "fp32_probe: bad argument");
+    jabd::fp32_probe_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, 1.0f, sink_dev);
+    JABD_LAUNCH_CHECK("fp32_probe_kernel");
+    return JABD_OK;
+}
 
 /* Test hook: compares fdiv_shared() with __fdiv_rn() on n pseudo-random operand pairs.  out_dev[0] receives the
  * number of mismatching results (out_dev[1] is scratch), first_bad_dev[4] = (a, d, got, expected) of one of them. */

@@ -590,6 +590,7 @@ int jabd_assign_match(const float *priors, int64_t P, const float *gt, const int
     assign_prep_kernel<<<(unsigned)B + n_tiles + 1u, kTile, 0, st>>>(gt, gt_off, reinterpret_cast<const float4 *>(priors), (int)P, B,
                                                                      (int)n_tiles, (int)grid, ws);
     JABD_LAUNCH_CHECK("assign_prep_kernel");
+    if (flags & JABD_ASSIGN_PREP_ONLY) return JABD_OK;
     assign_match_kernel<<<(unsigned)grid, kMatchThreads, 0, st>>>(reinterpret_cast<const float4 *>(priors), (int)P, ws,
                                                           (flags & JABD_ASSIGN_DENSE) ? 1 : 0, (int)n_tiles);
     JABD_LAUNCH_CHECK("assign_match_kernel");
