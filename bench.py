@@ -168,6 +168,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
@@ -190,29 +191,34 @@ def main():
     pri = anchors.Anchors(config.cfg_mnet, image_size=IMAGE).get_anchors()
     P = int(pri.shape[0])
     sets = []
+    from jabd_b200 import sharding
     for s in range(SETS):
-        first = (rank * SETS + s) * BATCH
-        tg = synth.make_gt_batch(2, BATCH, IMAGE, first_image=first)
+        # step s%SETS processes the global batch of world*BATCH images [s*world*BATCH, (s+1)*world*BATCH); every rank
+        # generates the (cheap, seeded) GT of the whole batch and keeps its contiguous shard, cut so that the ranks'
+        # GT counts -- not their image counts -- are balanced (sharding.shard_bounds; cost ~ sum(G))
+        tg_all = synth.make_gt_batch(2, world * BATCH, IMAGE, first_image=s * world * BATCH)
+        tg, (lo, hi) = sharding.local_targets(tg_all, rank, world, balance=True)
+        nb = len(tg)
         gt, offs, offs_host = batched.pack_targets([t for t in tg], dev)
         sumG = int(gt.shape[0])
-        ws = _tensor.workspace(L.jabd_assign_workspace_bytes(BATCH, P, sumG), dev)
-        sets.append(dict(host=tg, gt=gt, offs=offs, sumG=sumG, ws=ws,
-                         loc=torch.empty((BATCH, P, 4), dtype=torch.float32, device=dev),
-                         conf=torch.empty((BATCH, P), dtype=torch.int64, device=dev),
-                         landm=torch.empty((BATCH, P, 10), dtype=torch.float32, device=dev)))
-    mean_g = sum(s["sumG"] for s in sets) / float(SETS * BATCH)
+        ws = _tensor.workspace(L.jabd_assign_workspace_bytes(nb, P, sumG), dev)
+        sets.append(dict(host=tg, gt=gt, offs=offs, sumG=sumG, ws=ws, B=nb,
+                         loc=torch.empty((nb, P, 4), dtype=torch.float32, device=dev),
+                         conf=torch.empty((nb, P), dtype=torch.int64, device=dev),
+                         landm=torch.empty((nb, P, 10), dtype=torch.float32, device=dev)))
+    mean_g = sum(s["sumG"] for s in sets) / float(sum(s["B"] for s in sets))
 
     def assign(s, flags=0, st=None):
-        _lib.call("jabd_assign", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), BATCH, s["sumG"], THR, VAR[0], VAR[1], 0, 1, flags,
+        _lib.call("jabd_assign", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], THR, VAR[0], VAR[1], 0, 1, flags,
                   ptr(s["loc"]), ptr(s["conf"]), ptr(s["landm"]), None, None, None, None, ptr(s["ws"]), s["ws"].numel(),
                   ctypes.c_void_p((st or torch.cuda.current_stream(dev)).cuda_stream))
 
     def phase_match(s, flags=0):
-        _lib.call("jabd_assign_match", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), BATCH, s["sumG"], flags, ptr(s["ws"]),
+        _lib.call("jabd_assign_match", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], flags, ptr(s["ws"]),
                   s["ws"].numel(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
 
     def phase_encode(s):
-        _lib.call("jabd_assign_encode", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), BATCH, s["sumG"], THR, VAR[0], VAR[1], 0, 1,
+        _lib.call("jabd_assign_encode", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], THR, VAR[0], VAR[1], 0, 1,
                   ptr(s["loc"]), ptr(s["conf"]), ptr(s["landm"]), None, None, None, None, ptr(s["ws"]), s["ws"].numel(),
                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
 
@@ -279,7 +285,8 @@ def main():
     sum_g = sum(s["sumG"] for s in sets) / SETS
     pairs = float(P) * sum_g                                   # prior x GT pairs per launch
     flops_launch = 14.0 * pairs                                # 14 fp32 ops per pair, no FMA
-    bytes_step = BATCH * (80.0 * P) + 60.0 * sum_g             # 80P + 60G per image
+    mean_b = sum(s["B"] for s in sets) / float(SETS)          # == BATCH on one GPU; GT-balanced shards vary by a few images
+    bytes_step = mean_b * (80.0 * P) + 60.0 * sum_g            # 80P + 60G per image
 
     # measured FP32 (non-FMA) peak: dependency-free FMUL/FADD chains on every SM, same clocks as the run
     sms = ctypes.c_int(0)
@@ -330,19 +337,29 @@ def main():
         phases["match_dense_frac_of_fp32_measured"] = phases["match_dense_tflops"] / fp32_peak
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region
-    host = batched.HostAssign(pri, BATCH, max(s["sumG"] for s in sets))
+    # (fixed BATCH images per rank and step here: the transfer volume, which bounds this path, is set by B*P)
+    host_sets = [synth.make_gt_batch(2, BATCH, IMAGE, first_image=(rank * SETS + s_) * BATCH) for s_ in range(SETS)]
+    host = batched.HostAssign(pri, BATCH, max(sum(int(t.shape[0]) for t in hs) for hs in host_sets))
     n_e2e = min(K, 100)
     for k in range(3):
-        host(sets[k % SETS]["host"])
-    ms_e2e, _ = timed_loop(lambda k: host(sets[k % SETS]["host"]), n_e2e)
+        host(host_sets[k % SETS])
+    ms_e2e, _ = timed_loop(lambda k: host(host_sets[k % SETS]), n_e2e)
     e2e_value = world * BATCH * n_e2e / (ms_e2e / 1e3)
     # variant: targets stay on the GPU (what a training loop consumes), only the positives count comes back
-    pin_gt = [torch.cat(s["host"], 0).pin_memory() for s in sets]
+    dsets = []
+    for hs in host_sets:
+        gt_d, offs_d, _ = batched.pack_targets(hs, dev)
+        sg = int(gt_d.shape[0])
+        dsets.append(dict(gt=gt_d, offs=offs_d, sumG=sg, B=BATCH, pin=torch.cat(hs, 0).pin_memory(),
+                          ws=_tensor.workspace(L.jabd_assign_workspace_bytes(BATCH, P, sg), dev),
+                          loc=torch.empty((BATCH, P, 4), dtype=torch.float32, device=dev),
+                          conf=torch.empty((BATCH, P), dtype=torch.int64, device=dev),
+                          landm=torch.empty((BATCH, P, 10), dtype=torch.float32, device=dev)))
     pin_cnt = torch.empty((BATCH,), dtype=torch.int64).pin_memory()
 
     def e2e_device_out(k):
-        s = sets[k % SETS]
-        s["gt"].copy_(pin_gt[k % SETS], non_blocking=True)
+        s = dsets[k % SETS]
+        s["gt"].copy_(s["pin"], non_blocking=True)
         assign(s)
         pin_cnt.copy_((s["conf"] != 0).sum(1), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
@@ -354,7 +371,7 @@ def main():
            "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
            "api": "batched.HostAssign -> jabd_assign_host: pinned GT in, all three target tensors out to pinned host memory",
            "device_resident_targets": {"value": world * BATCH * n_e2e / (ms_e2e_dev / 1e3), "unit": "images/s",
-                                       "h2d_bytes_per_step": int(pin_gt[0].numel() * 4), "d2h_bytes_per_step": BATCH * 8,
+                                       "h2d_bytes_per_step": int(dsets[0]["pin"].numel() * 4), "d2h_bytes_per_step": BATCH * 8,
                                        "note": "GT H2D + assign + per-image positive count D2H; targets stay in HBM for the loss"}}
 
     # ---- inference side: decode+top-k+NMS at 640^2 (the metric's second half) and at cfg3's 1024^2
@@ -394,7 +411,14 @@ def main():
                           ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
             for k in range(4):
                 dec(k)
-            ms_dec, _ = timed_loop(dec, 50)
+            torch.cuda.synchronize(dev)
+            g_dec = torch.cuda.CUDAGraph()              # 4 launches per replay: the host never limits a ~10 us kernel
+            with torch.cuda.graph(g_dec):
+                for k in range(4):
+                    dec(k)
+            g_dec.replay()
+            ms_dec, _ = timed_loop(lambda k: g_dec.replay(), 50)
+            ms_dec /= 4.0
             gbs = 64 * Pd * 32.0 / (ms_dec / 50 * 1e-3) / 1e9
             detect_info[name]["decode_kernel"] = {"batch": 64, "GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
                                                   "bytes_per_launch": 64 * Pd * 32.0, "us": ms_dec / 50 * 1e3,

@@ -140,13 +140,23 @@ __global__ void __launch_bounds__(256) landm_kernel(const float2 *__restrict__ i
     out[img + e] = o;
 }
 
+// D1 for a batch: thread = one prior for kDecImgs consecutive images -- the prior is read once, the kDecImgs loc
+// vectors are independent 16-byte loads in flight together, stores are 16-byte and coalesced along the prior axis.
+constexpr int kDecImgs = 4;
 __global__ void __launch_bounds__(256) decode_kernel(const float4 *__restrict__ loc, const float4 *__restrict__ priors, long long P,
-                                                     float var0, float var1, float4 *__restrict__ out)
+                                                     int batch, float var0, float var1, float4 *__restrict__ out)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    const long long i = (long long)blockIdx.y * P + p;
-    out[i] = decode_box(__ldg(loc + i), __ldg(priors + p), var0, var1);
+    const int b0 = blockIdx.y * kDecImgs;
+    const float4 pr = __ldg(priors + p);
+    float4 l[kDecImgs];
+#pragma unroll
+    for (int k = 0; k < kDecImgs; ++k)
+        if (b0 + k < batch) l[k] = __ldcs(loc + (long long)(b0 + k) * P + p); // streamed once: evict-first
+#pragma unroll
+    for (int k = 0; k < kDecImgs; ++k)
+        if (b0 + k < batch) __stcs(out + (long long)(b0 + k) * P + p, decode_box(l[k], pr, var0, var1));
 }
 
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -275,10 +285,10 @@ int jabd_decode(const float *loc, const float *priors, int64_t P, int batch, flo
     JABD_REQUIRE(loc && priors && out, JABD_EINVAL, "decode: null pointer");
     JABD_REQUIRE(aligned_to(loc, 16) && aligned_to(priors, 16) && aligned_to(out, 16), JABD_EALIGN,
                  "decode: 16-byte alignment required");
-    const dim3 grid(blocks_for(P, 256), (unsigned)batch);
+    const dim3 grid(blocks_for(P, 256), (unsigned)((batch + kDecImgs - 1) / kDecImgs));
     decode_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4 *>(loc),
-                                                                       reinterpret_cast<const float4 *>(priors), P, var0, var1,
-                                                                       reinterpret_cast<float4 *>(out));
+                                                                       reinterpret_cast<const float4 *>(priors), P, batch, var0,
+                                                                       var1, reinterpret_cast<float4 *>(out));
     JABD_LAUNCH_CHECK("decode_kernel");
     return JABD_OK;
 }
