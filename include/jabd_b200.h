@@ -55,6 +55,8 @@ enum {
 /* flags for jabd_assign */
 #define JABD_ASSIGN_DENSE 1 /* evaluate every prior x GT pair (no spatial culling); same results */
 #define JABD_ASSIGN_PREP_ONLY 2 /* jabd_assign_match only: launch the staging kernel alone (per-kernel timing) */
+#define JABD_ASSIGN_ASYNC 4 /* jabd_assign_host only: do not synchronise; host buffers must be pinned and the caller
+                               synchronises `stream` (or an event recorded on it) before reading the outputs */
 
 JABD_API int jabd_version(void);
 JABD_API const char *jabd_last_error(void);
@@ -124,7 +126,8 @@ JABD_API int jabd_assign_encode(const float *priors, int64_t P, const float *gt,
                                 jabd_stream_t stream);
 /* Same call with HOST buffers (pageable or pinned): copies gt/gt_off in, runs jabd_assign, copies the
  * three target tensors out.  priors and the staging area stay on the device:
- * dev_scratch must hold jabd_assign_host_scratch_bytes().  Synchronises `stream` before returning. */
+ * dev_scratch must hold jabd_assign_host_scratch_bytes().  Synchronises `stream` before returning unless
+ * JABD_ASSIGN_ASYNC is set (two calls on two streams with two scratch areas then overlap copies and kernels). */
 JABD_API size_t jabd_assign_host_scratch_bytes(int B, int64_t P, int64_t sumG, int with_landm);
 JABD_API int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, const int *gt_off_host, int B,
                               float threshold, float var0, float var1, int label_mode, int encode_mode, int flags,

@@ -21,6 +21,7 @@ __all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "d
 
 THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
 FLAG_DENSE = 1
+FLAG_ASYNC = 4
 
 
 def pack_targets(targets, device):
@@ -138,43 +139,70 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
 
 
 class HostAssign(object):
-    """End-to-end host-buffer path (``jabd_assign_host``): pinned staging buffers and the device scratch are
-    allocated once for a (B, P, max sumG) shape; each call copies GT in, assigns, copies the targets out."""
+    """End-to-end host-buffer path (``jabd_assign_host``) for a fixed (B, P, max sumG) shape: pinned staging buffers and
+    the device scratch are allocated once; each call copies GT in, assigns, copies the three target tensors out.
 
-    def __init__(self, priors, B, max_sum_g, with_landm=True, device=None):
+    ``h(targets)`` is synchronous.  ``submit`` / ``wait`` expose the same call as a ``depth``-slot pipeline (one
+    stream, scratch area and pinned output set per slot, ``JABD_ASSIGN_ASYNC``): while slot k's 34 MB of targets
+    drain over PCIe, slot k+1's GT upload and kernels already run.  The tensors returned by ``wait(slot)`` stay
+    valid until that slot is submitted again."""
+
+    def __init__(self, priors, B, max_sum_g, with_landm=True, device=None, depth=2):
         _tensor.require_cuda()
         self.dev = torch.device(device) if device is not None else _tensor.device_of(priors)
         self.pri = _tensor.to_dev(priors, self.dev)
         self.B, self.P, self.cap = int(B), int(self.pri.shape[0]), int(max_sum_g)
+        self.with_landm = bool(with_landm)
         L = _lib.lib()
-        self.scratch = _tensor.workspace(L.jabd_assign_host_scratch_bytes(self.B, self.P, self.cap, 1 if with_landm else 0), self.dev)
-        self.gt_pin = torch.empty((self.cap, 15), dtype=torch.float32).pin_memory()
-        self.off_pin = torch.empty((self.B + 1,), dtype=torch.int32).pin_memory()
-        self.loc_t = torch.empty((self.B, self.P, 4), dtype=torch.float32).pin_memory()
-        self.conf_t = torch.empty((self.B, self.P), dtype=torch.int64).pin_memory()
-        self.landm_t = torch.empty((self.B, self.P, 10), dtype=torch.float32).pin_memory() if with_landm else None
+        nbytes = L.jabd_assign_host_scratch_bytes(self.B, self.P, self.cap, 1 if with_landm else 0)
+        self.slots = []
+        for _ in range(max(int(depth), 1)):
+            self.slots.append(dict(
+                scratch=_tensor.workspace(nbytes, self.dev),
+                gt=torch.empty((self.cap, 15), dtype=torch.float32).pin_memory(),
+                off=torch.empty((self.B + 1,), dtype=torch.int32).pin_memory(),
+                loc_t=torch.empty((self.B, self.P, 4), dtype=torch.float32).pin_memory(),
+                conf_t=torch.empty((self.B, self.P), dtype=torch.int64).pin_memory(),
+                landm_t=torch.empty((self.B, self.P, 10), dtype=torch.float32).pin_memory() if with_landm else None,
+                stream=torch.cuda.Stream(self.dev), done=torch.cuda.Event()))
+        self.next_slot = 0
+        self.last_h2d = self.last_d2h = 0
 
-    def __call__(self, targets, threshold=0.35, variances=(0.1, 0.2), label_mode=0, encode=True, dense=False):
-        off = 0
-        self.off_pin[0] = 0
+    def submit(self, targets, threshold=0.35, variances=(0.1, 0.2), label_mode=0, encode=True, dense=False):
+        """Enqueue one batch on the next slot; returns the slot id for ``wait``."""
         if len(targets) != self.B:
             raise ValueError("expected %d images" % self.B)
-        for i, t in enumerate(targets):
-            g = int(t.shape[0])
-            if off + g > self.cap:
-                raise ValueError("sumG exceeds the capacity this HostAssign was built for")
-            self.gt_pin[off:off + g].copy_(torch.as_tensor(t))
-            off += g
-            self.off_pin[i + 1] = off
+        k = self.next_slot
+        self.next_slot = (k + 1) % len(self.slots)
+        sl = self.slots[k]
+        sl["done"].synchronize()            # the slot's previous outputs may still be in flight
+        counts = [int(t.shape[0]) for t in targets]
+        total = sum(counts)
+        if total > self.cap:
+            raise ValueError("sumG exceeds the capacity this HostAssign was built for")
+        if total:
+            torch.cat([torch.as_tensor(t, dtype=torch.float32) for t in targets if t.shape[0]], 0, out=sl["gt"][:total])
+        offs = sl["off"]
+        offs[0] = 0
+        torch.cumsum(torch.tensor(counts, dtype=torch.int32), 0, out=offs[1:])
         v0, v1 = _tensor.variances_of(variances)
         with torch.cuda.device(self.dev):
-            _lib.call("jabd_assign_host", ptr(self.pri), self.P, ptr(self.gt_pin), ptr(self.off_pin), self.B, float(threshold),
-                      v0, v1, int(label_mode), 1 if encode else 0, FLAG_DENSE if dense else 0, ptr(self.loc_t),
-                      ptr(self.conf_t), ptr(self.landm_t), ptr(self.scratch), self.scratch.numel(),
-                      _tensor.stream_of(self.dev))
-        self.last_h2d = off * 15 * 4 + (self.B + 1) * 4
-        self.last_d2h = self.B * self.P * (16 + 8 + (40 if self.landm_t is not None else 0))
-        return self.loc_t, self.conf_t, self.landm_t
+            _lib.call("jabd_assign_host", ptr(self.pri), self.P, ptr(sl["gt"]), ptr(offs), self.B, float(threshold),
+                      v0, v1, int(label_mode), 1 if encode else 0, (FLAG_DENSE if dense else 0) | FLAG_ASYNC, ptr(sl["loc_t"]),
+                      ptr(sl["conf_t"]), ptr(sl["landm_t"]), ptr(sl["scratch"]), sl["scratch"].numel(),
+                      ctypes.c_void_p(sl["stream"].cuda_stream))
+            sl["done"].record(sl["stream"])
+        self.last_h2d = total * 15 * 4 + (self.B + 1) * 4
+        self.last_d2h = self.B * self.P * (16 + 8 + (40 if self.with_landm else 0))
+        return k
+
+    def wait(self, slot):
+        sl = self.slots[slot]
+        sl["done"].synchronize()
+        return sl["loc_t"], sl["conf_t"], sl["landm_t"]
+
+    def __call__(self, targets, **kw):
+        return self.wait(self.submit(targets, **kw))
 
 
 def assign_targets_host(priors, targets, **kw):

@@ -687,14 +687,15 @@ int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, c
     const size_t ws_bytes = dev_scratch_bytes - off;
     if (sumG > 0) JABD_CUDA(cudaMemcpyAsync(d_gt, gt_host, sizeof(float) * JABD_GT_ROW * (size_t)sumG, cudaMemcpyHostToDevice, st));
     JABD_CUDA(cudaMemcpyAsync(d_off, gt_off_host, sizeof(int) * (size_t)(B + 1), cudaMemcpyHostToDevice, st));
-    int rc = jabd_assign(priors_dev, P, d_gt, d_off, B, sumG, threshold, var0, var1, label_mode, encode_mode, flags, d_loc,
+    int rc = jabd_assign(priors_dev, P, d_gt, d_off, B, sumG, threshold, var0, var1, label_mode, encode_mode,
+                         flags & JABD_ASSIGN_DENSE, d_loc,
                          d_conf, d_landm, nullptr, nullptr, nullptr, nullptr, d_ws, ws_bytes, stream);
     if (rc != JABD_OK) return rc;
     JABD_CUDA(cudaMemcpyAsync(loc_t_host, d_loc, sizeof(float) * 4 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
     JABD_CUDA(cudaMemcpyAsync(conf_t_host, d_conf, sizeof(int64_t) * (size_t)B * P, cudaMemcpyDeviceToHost, st));
     if (with_landm)
         JABD_CUDA(cudaMemcpyAsync(landm_t_host, d_landm, sizeof(float) * 10 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
-    JABD_CUDA(cudaStreamSynchronize(st));
+    if (!(flags & JABD_ASSIGN_ASYNC)) JABD_CUDA(cudaStreamSynchronize(st));
     return JABD_OK;
 }
 
