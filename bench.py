@@ -138,12 +138,28 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------- main arm
+def emit(line):
+    """Print the one JSON line on the real stdout (see main(): fd 1 is pointed at stderr while the run lasts, so that
+    banners printed by C libraries -- NCCL's version line, for one -- cannot land in front of it)."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    sys.stdout.flush()
+    os.write(fd, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
@@ -482,7 +498,7 @@ def main():
         "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "phases": phases,
         "detect": detect_info,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 

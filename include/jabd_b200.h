@@ -134,6 +134,26 @@ JABD_API int jabd_assign_host(const float *priors_dev, int64_t P, const float *g
                               float *loc_t_host, int64_t *conf_t_host, float *landm_t_host, void *dev_scratch,
                               size_t dev_scratch_bytes, jabd_stream_t stream);
 
+/* ---- the rest of MultiBoxLoss.forward (R/nets/retinaface_training.py:229-303) on the assigned
+ * targets: positives, hard-negative mining (per-image radix select of the min(negpos_ratio*num_pos, P-1) largest
+ * rank values instead of the reference's two full sorts, :270-281), smooth-L1 sums for boxes and landmarks,
+ * cross-entropy over positives + mined negatives, normalisation.  num_classes == 2.
+ *   loc_data [B,P,4], conf_data [B,P,2] (logits), landm_data [B,P,10]: the network outputs;
+ *   loc_t / conf_t / landm_t: outputs of jabd_assign;
+ *   losses[3] = loss_l, loss_c, loss_landm; norms[2] = N, N1 (:293, :299); sel_mask [B,P] u8: bit0 pos (conf_t != 0),
+ *   bit1 pos1 (conf_t > 0), bit2 mined negative -- kept for the backward pass.
+ * _backward writes d(sum_k grad_losses[k] * losses[k]) / d(loc_data, conf_data, landm_data) (dense, zeros elsewhere);
+ * grad_losses[3] is device memory. */
+JABD_API size_t jabd_multibox_loss_workspace_bytes(int B);
+JABD_API int jabd_multibox_loss_forward(const float *loc_data, const float *conf_data, const float *landm_data,
+                                        const float *loc_t, const int64_t *conf_t, const float *landm_t, int B, int64_t P,
+                                        int negpos_ratio, float *losses, float *norms, unsigned char *sel_mask,
+                                        void *workspace, size_t workspace_bytes, jabd_stream_t stream);
+JABD_API int jabd_multibox_loss_backward(const float *loc_data, const float *conf_data, const float *landm_data,
+                                         const float *loc_t, const float *landm_t, const unsigned char *sel_mask,
+                                         const float *norms, const float *grad_losses, int B, int64_t P, float *g_loc,
+                                         float *g_conf, float *g_landm, jabd_stream_t stream);
+
 /* ---- S1/K1/N1/N2: score threshold, top-k, greedy NMS ---------------------------------------------- */
 /* thresh_mode: 0 = none, 1 = score >= conf_thres (R/utils/utils_bbox.py:266), 2 = score > conf_thres. */
 /* nms_mode: 0 = torchvision.ops.nms semantics (call site R/utils/utils_bbox.py:275-279): stable descending

@@ -17,7 +17,7 @@ import torch
 from . import _lib, _tensor
 from ._tensor import ptr
 
-__all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "detect_host"]
+__all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "detect_host", "multibox_loss"]
 
 THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
 FLAG_DENSE = 1
@@ -136,6 +136,59 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
                   THRESH_GT if strict else THRESH_GE, int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), keep_cap,
                   ptr(dets), ptr(counts), ptr(keep_idx), ptr(ws), ws.numel(), _tensor.stream_of(dev))
     return dets, counts, keep_idx
+
+
+class _MultiBoxLossFn(torch.autograd.Function):
+    """Hard-negative mining + the three loss reductions of ``MultiBoxLoss.forward``
+    (R/nets/retinaface_training.py:229-303) as one autograd node over the network outputs."""
+
+    @staticmethod
+    def forward(ctx, loc_data, conf_data, landm_data, loc_t, conf_t, landm_t, negpos_ratio):
+        dev = loc_data.device
+        B, P = int(loc_data.shape[0]), int(loc_data.shape[1])
+        ld, cd, md = (t.detach().contiguous().float() for t in (loc_data, conf_data, landm_data))
+        losses = torch.empty((3,), dtype=torch.float32, device=dev)
+        norms = torch.empty((2,), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, P), dtype=torch.uint8, device=dev)
+        L = _lib.lib()
+        ws = _tensor.workspace(L.jabd_multibox_loss_workspace_bytes(B), dev)
+        with torch.cuda.device(dev):
+            _lib.call("jabd_multibox_loss_forward", ptr(ld), ptr(cd), ptr(md), ptr(loc_t), ptr(conf_t), ptr(landm_t), B, P,
+                      int(negpos_ratio), ptr(losses), ptr(norms), ptr(mask), ptr(ws), ws.numel(), _tensor.stream_of(dev))
+        ctx.save_for_backward(ld, cd, md, loc_t, landm_t, mask, norms)
+        ctx.mark_non_differentiable(mask, norms)
+        return losses[0], losses[1], losses[2], mask, norms
+
+    @staticmethod
+    def backward(ctx, g_l, g_c, g_landm, _gm, _gn):
+        ld, cd, md, loc_t, landm_t, mask, norms = ctx.saved_tensors
+        dev = ld.device
+        B, P = int(ld.shape[0]), int(ld.shape[1])
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        g = torch.stack([(x if x is not None else zero).to(dev, torch.float32).reshape(()) for x in (g_l, g_c, g_landm)]).contiguous()
+        g_loc, g_conf, g_lm = torch.empty_like(ld), torch.empty_like(cd), torch.empty_like(md)
+        with torch.cuda.device(dev):
+            _lib.call("jabd_multibox_loss_backward", ptr(ld), ptr(cd), ptr(md), ptr(loc_t), ptr(landm_t), ptr(mask), ptr(norms),
+                      ptr(g), B, P, ptr(g_loc), ptr(g_conf), ptr(g_lm), _tensor.stream_of(dev))
+        return g_loc, g_conf, g_lm, None, None, None, None
+
+
+def multibox_loss(predictions, loc_t, conf_t, landm_t, negpos_ratio=7, return_aux=False):
+    """``(loss_l, loss_c, loss_landm)`` of R/nets/retinaface_training.py:229-303 for CUDA predictions
+    ``(loc_data [B,P,4], conf_data [B,P,2] logits, landm_data [B,P,10])`` and the targets of ``assign_targets``.
+    Differentiable w.r.t. the predictions.  ``return_aux`` adds the selection mask ``[B,P]`` u8 (bit0 pos, bit1
+    pos1, bit2 mined negative) and ``(N, N1)``."""
+    loc_data, conf_data, landm_data = predictions
+    B, P = int(loc_data.shape[0]), int(loc_data.shape[1])
+    if not loc_data.is_cuda:
+        raise RuntimeError("multibox_loss needs CUDA predictions; there is no CPU path")
+    if tuple(conf_data.shape) != (B, P, 2) or tuple(landm_data.shape) != (B, P, 10) or tuple(loc_data.shape) != (B, P, 4):
+        raise ValueError("expected loc_data [B,P,4], conf_data [B,P,2] (num_classes == 2), landm_data [B,P,10]")
+    for t, shp, dt in ((loc_t, (B, P, 4), torch.float32), (conf_t, (B, P), torch.int64), (landm_t, (B, P, 10), torch.float32)):
+        if not (t.is_cuda and t.is_contiguous() and tuple(t.shape) == shp and t.dtype == dt):
+            raise ValueError("targets must be the contiguous CUDA tensors returned by assign_targets")
+    l, c, m, mask, norms = _MultiBoxLossFn.apply(loc_data, conf_data, landm_data, loc_t, conf_t, landm_t, int(negpos_ratio))
+    return (l, c, m, mask, norms) if return_aux else (l, c, m)
 
 
 class HostAssign(object):

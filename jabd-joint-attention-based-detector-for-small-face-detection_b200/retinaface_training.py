@@ -12,9 +12,12 @@ call time (R/nets/retinaface_training.py:214), so::
 ``assign_batch`` is the batched replacement of the loop at :197-227.
 """
 from . import _ops
-from .batched import assign_targets
+import torch
 
-__all__ = ["point_form", "intersect", "jaccard", "encode", "encode_landm", "match", "match_iou", "assign_batch", "install"]
+from .batched import assign_targets, multibox_loss
+
+__all__ = ["point_form", "intersect", "jaccard", "encode", "encode_landm", "match", "match_iou", "assign_batch", "install",
+           "MultiBoxLoss"]
 
 
 def point_form(boxes):
@@ -59,10 +62,36 @@ def assign_batch(threshold, targets, priors, variances):
     return assign_targets(priors, targets, threshold=threshold, variances=variances)
 
 
+class MultiBoxLoss(torch.nn.Module):
+    """Drop-in for ``MultiBoxLoss`` (R/nets/retinaface_training.py:165-303): same constructor, same
+    ``forward(predictions, priors, targets) -> (loss_l, loss_c, loss_landm)``.  Target assignment is the three
+    batched launches of ``assign_batch``; positives, hard-negative mining (:259-281) and the loss sums (:229-301)
+    are ``batched.multibox_loss`` -- targets never leave the GPU and nothing is sorted."""
+
+    def __init__(self, num_classes, overlap_thresh, neg_pos, variance, cuda=True):
+        super(MultiBoxLoss, self).__init__()
+        if int(num_classes) != 2:
+            raise ValueError("MultiBoxLoss: num_classes must be 2 (face / background), like the reference's RetinaFace heads")
+        self.num_classes = int(num_classes)
+        self.threshold = overlap_thresh
+        self.negpos_ratio = neg_pos
+        self.variance = variance
+        self.cuda = cuda  # kept for signature parity; the computation always runs on the predictions' CUDA device
+
+    def forward(self, predictions, priors, targets):
+        loc_data = predictions[0]
+        with torch.no_grad():
+            loc_t, conf_t, landm_t = assign_targets(priors.data.to(loc_data.device), [t.data for t in targets],
+                                                    threshold=self.threshold, variances=self.variance)
+        return multibox_loss(predictions, loc_t, conf_t, landm_t, self.negpos_ratio)
+
+
 def install(module):
     """Point the reference module's globals at these implementations (no edit of ``nets/``)."""
     for name in ("point_form", "intersect", "jaccard", "encode", "encode_landm", "match"):
         setattr(module, name, globals()[name])
     if hasattr(module, "match_iou"):
         module.match_iou = match_iou
+    if hasattr(module, "MultiBoxLoss"):
+        module.MultiBoxLoss = MultiBoxLoss
     return module

@@ -103,6 +103,16 @@ def make_preds_random(cfg_id, image_idx, num_priors):
     return loc.contiguous(), conf, landm.contiguous()
 
 
+def make_logits(cfg_id, image_idx, num_priors):
+    """Training-time network outputs for one image (inputs of MultiBoxLoss.forward, R/nets/retinaface_training.py:183):
+    loc ~ N(0, 0.5^2) [P,4], class logits ~ N(0, 1.5^2) [P,2], landm ~ N(0, 1) [P,10].  Seed 3000*cfg_id + image_idx."""
+    g = _gen(3000 * int(cfg_id) + int(image_idx))
+    loc = torch.randn((num_priors, 4), generator=g) * 0.5
+    conf = torch.randn((num_priors, 2), generator=g) * 1.5
+    landm = torch.randn((num_priors, 10), generator=g)
+    return loc.contiguous(), conf.contiguous(), landm.contiguous()
+
+
 def dense_iou_for_synthesis(truths, priors):
     """Plain broadcast IoU used only to *shape* the clustered predictions."""
     pf = torch.cat([priors[:, :2] - priors[:, 2:] / 2, priors[:, :2] + priors[:, 2:] / 2], 1)

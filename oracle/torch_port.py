@@ -93,6 +93,48 @@ def assign_batch(thr, targets, priors, var):
     return loc_t, conf_t, landm_t
 
 
+def global_lse(x):
+    """log_sum_exp with the maximum of the WHOLE tensor; R/nets/retinaface_training.py:86-88."""
+    m = x.data.max()
+    return torch.log(torch.sum(torch.exp(x - m), 1, keepdim=True)) + m
+
+
+def multibox_loss(predictions, priors, targets, thr=0.35, var=(0.1, 0.2), negpos_ratio=7, return_aux=False):
+    """MultiBoxLoss.forward with cuda=False; R/nets/retinaface_training.py:183-303.  ``predictions`` =
+    (loc_data [B,P,4], conf_data [B,P,2], landm_data [B,P,10]) CPU tensors (may require grad)."""
+    import torch.nn.functional as F
+    loc_data, conf_data, landm_data = predictions
+    n = loc_data.size(0)
+    loc_t, conf_t, landm_t = assign_batch(thr, [t.data for t in targets], priors.data, list(var))
+    zero = torch.tensor(0)
+    lm_pos = conf_t > zero                                           # :243
+    lm_sel = lm_pos.unsqueeze(lm_pos.dim()).expand_as(landm_data)
+    loss_landm = F.smooth_l1_loss(landm_data[lm_sel].view(-1, 10), landm_t[lm_sel].view(-1, 10), reduction='sum')
+    pos = conf_t != zero                                             # :250
+    box_sel = pos.unsqueeze(pos.dim()).expand_as(loc_data)
+    loss_l = F.smooth_l1_loss(loc_data[box_sel].view(-1, 4), loc_t[box_sel].view(-1, 4), reduction='sum')
+    conf_t[pos] = 1                                                  # :259
+    flat = conf_data.view(-1, 2)
+    rank_val = global_lse(flat) - flat.gather(1, conf_t.view(-1, 1)) # :265
+    rank_val[pos.view(-1, 1)] = 0
+    rank_val = rank_val.view(n, -1)
+    _, order = rank_val.sort(1, descending=True)                     # :270-271
+    _, rank = order.sort(1)
+    num_pos = pos.long().sum(1, keepdim=True)
+    num_neg = torch.clamp(negpos_ratio * num_pos, max=pos.size(1) - 1)
+    neg = rank < num_neg.expand_as(rank)
+    both = (pos.unsqueeze(2).expand_as(conf_data) + neg.unsqueeze(2).expand_as(conf_data)).gt(0)
+    loss_c = F.cross_entropy(conf_data[both].view(-1, 2), conf_t[(pos + neg).gt(0)], reduction='sum')
+    N = max(num_pos.data.sum().float(), 1)
+    loss_l = loss_l / N
+    loss_c = loss_c / N
+    N1 = max(lm_pos.long().sum(1, keepdim=True).data.sum().float(), 1)
+    loss_landm = loss_landm / N1
+    if return_aux:
+        return loss_l, loss_c, loss_landm, dict(pos=pos, pos1=lm_pos, neg=neg, N=float(N), N1=float(N1), rank_val=rank_val.detach())
+    return loss_l, loss_c, loss_landm
+
+
 def decode_boxes(loc, p, var):
     """R/utils/utils_bbox.py:29-34."""
     b = torch.cat((p[:, :2] + loc[:, :2] * var[0] * p[:, 2:],

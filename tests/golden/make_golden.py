@@ -395,6 +395,49 @@ def check(R):
     return n_bad
 
 
+# ----------------------------------------------------------------------------- MultiBox loss
+LOSS_CASES = [("s160", (160, 160), 3, 12), ("s640", (640, 640), 2, None)]
+
+
+def loss_inputs(r_anchors, cfg, size, batch, count, cfg_id=6):
+    with contextlib.redirect_stdout(io.StringIO()):
+        pri = r_anchors.Anchors(cfg, image_size=size).get_anchors()
+    P = pri.shape[0]
+    targets = [synth.make_gt(cfg_id, i, size, count=count) for i in range(batch)]
+    preds = [synth.make_logits(cfg_id, i, P) for i in range(batch)]
+    loc = torch.stack([p[0] for p in preds]).requires_grad_(True)
+    conf = torch.stack([p[1] for p in preds]).requires_grad_(True)
+    landm = torch.stack([p[2] for p in preds]).requires_grad_(True)
+    return pri, targets, (loc, conf, landm)
+
+
+def gen_loss(R):
+    """MultiBoxLoss.forward + backward of the reference (cuda=False) on seeded logits and GT."""
+    r_anchors, r_config, _, _, r_training, _ = R
+    out = {}
+    for tag, size, batch, count in LOSS_CASES:
+        pri, targets, preds = loss_inputs(r_anchors, r_config.cfg_mnet, size, batch, count)
+        crit = r_training.MultiBoxLoss(2, THR, 7, VAR, False)
+        l, c, m = crit(preds, pri, targets)
+        (1.0 * l + 2.0 * c + 0.5 * m).backward()
+        out[tag + "_losses"] = np.array([l.item(), c.item(), m.item()], dtype=np.float32)
+        g_loc, g_conf, g_landm = (p.grad.numpy() for p in preds)
+        out[tag + "_sel"] = np.packbits((np.abs(g_conf).sum(2) != 0))       # priors that enter loss_c (pos | mined neg)
+        out[tag + "_gsum"] = np.array([np.abs(g_loc).sum(), np.abs(g_conf).sum(), np.abs(g_landm).sum()], dtype=np.float64)
+        if tag == "s160":
+            out[tag + "_g_loc"], out[tag + "_g_conf"], out[tag + "_g_landm"] = g_loc, g_conf, g_landm
+        else:
+            out[tag + "_g_loc_sha"], out[tag + "_g_landm_sha"] = sha(g_loc), sha(g_landm)
+            nz = np.flatnonzero(np.abs(g_conf).sum(2).reshape(-1))
+            out[tag + "_g_conf_nz_idx"] = nz.astype(np.int32)
+            out[tag + "_g_conf_nz"] = g_conf.reshape(-1, 2)[nz]
+            nzl = np.flatnonzero(np.abs(g_loc).sum(2).reshape(-1))
+            out[tag + "_g_loc_nz_idx"] = nzl.astype(np.int32)
+            out[tag + "_g_loc_nz"] = g_loc.reshape(-1, 4)[nzl]
+            out[tag + "_g_landm_nz"] = g_landm.reshape(-1, 10)[nzl]
+    save("loss.npz", **out)
+
+
 def main():
     R = import_reference()
     gen_priors(R)
@@ -402,6 +445,7 @@ def main():
     gen_decode(R)
     gen_nms(R)
     gen_pipeline(R)
+    gen_loss(R)
     if "--check" in sys.argv:
         sys.exit(1 if check(R) else 0)
 

@@ -213,3 +213,35 @@ def test_pipeline_dropin_and_topk(tag, gen):
         d2, i2 = tp.infer_one_topk(torch.from_numpy(loc), torch.from_numpy(conf), torch.from_numpy(landm),
                                    torch.from_numpy(pri), VAR, ct, topk, nt, keepk)
         assert np.array_equal(i2.numpy(), g[k2 + "idx"]) and np.array_equal(d2.numpy(), g[k2 + "dets"])
+
+
+# ------------------------------------------------------------------ MultiBox loss
+LOSS_CASES = [("s160", (160, 160), 3, 12), ("s640", (640, 640), 2, None)]
+
+
+def _loss_inputs(size, batch, count, cfg_id=6):
+    from jabd_b200 import synth
+    pri = torch.from_numpy(orc.priors(cfgs.cfg_mnet, size))
+    P = pri.shape[0]
+    targets = [synth.make_gt(cfg_id, i, size, count=count) for i in range(batch)]
+    preds = [synth.make_logits(cfg_id, i, P) for i in range(batch)]
+    return pri, targets, tuple(torch.stack([p[k] for p in preds]).requires_grad_(True) for k in range(3))
+
+
+@pytest.mark.parametrize("tag,size,batch,count", LOSS_CASES)
+def test_multibox_loss_torch_port(tag, size, batch, count):
+    """oracle/torch_port.multibox_loss == the reference's MultiBoxLoss (forward values, selection, gradients)."""
+    g = load_golden("loss.npz")
+    pri, targets, preds = _loss_inputs(size, batch, count)
+    l, c, m = tp.multibox_loss(preds, pri, targets, 0.35, [0.1, 0.2], 7)
+    (1.0 * l + 2.0 * c + 0.5 * m).backward()
+    np.testing.assert_array_equal(np.array([l.item(), c.item(), m.item()], dtype=np.float32), g[tag + "_losses"])
+    g_loc, g_conf, g_landm = (p.grad.numpy() for p in preds)
+    np.testing.assert_array_equal(np.packbits(np.abs(g_conf).sum(2) != 0), g[tag + "_sel"])
+    if tag == "s160":
+        np.testing.assert_array_equal(g_loc, g[tag + "_g_loc"])
+        np.testing.assert_array_equal(g_conf, g[tag + "_g_conf"])
+        np.testing.assert_array_equal(g_landm, g[tag + "_g_landm"])
+    else:
+        np.testing.assert_array_equal(sha(g_loc), g[tag + "_g_loc_sha"])
+        np.testing.assert_array_equal(g_conf.reshape(-1, 2)[g[tag + "_g_conf_nz_idx"]], g[tag + "_g_conf_nz"])
