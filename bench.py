@@ -403,6 +403,54 @@ def main():
                                        "h2d_bytes_per_step": int(dsets[0]["pin"].numel() * 4), "d2h_bytes_per_step": BATCH * 8,
                                        "note": "GT H2D + assign + per-image positive count D2H; targets stay in HBM for the loss"}}
 
+    # ---- the whole MultiBoxLoss.forward + backward on the device (assign -> mining -> sums -> grads)
+    loss_info = None
+    if not args.no_extras:
+        ds0 = dsets[0]
+        preds_l = [synth.make_logits(2, i, P) for i in range(BATCH)]
+        pl, pc, pm = (torch.stack([q[j] for q in preds_l]).to(dev) for j in range(3))
+        losses = torch.empty((3,), dtype=torch.float32, device=dev)
+        norms = torch.empty((2,), dtype=torch.float32, device=dev)
+        lmask = torch.empty((BATCH, P), dtype=torch.uint8, device=dev)
+        lws = _tensor.workspace(L.jabd_multibox_loss_workspace_bytes(BATCH), dev)
+        gl, gc, gm = torch.empty_like(pl), torch.empty_like(pc), torch.empty_like(pm)
+        gin = torch.ones((3,), dtype=torch.float32, device=dev)
+
+        def loss_step():
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            assign(ds0)
+            _lib.call("jabd_multibox_loss_forward", ptr(pl), ptr(pc), ptr(pm), ptr(ds0["loc"]), ptr(ds0["conf"]), ptr(ds0["landm"]),
+                      BATCH, P, 7, ptr(losses), ptr(norms), ptr(lmask), ptr(lws), lws.numel(), st)
+            _lib.call("jabd_multibox_loss_backward", ptr(pl), ptr(pc), ptr(pm), ptr(ds0["loc"]), ptr(ds0["landm"]), ptr(lmask),
+                      ptr(norms), ptr(gin), BATCH, P, ptr(gl), ptr(gc), ptr(gm), st)
+        loss_step()
+        torch.cuda.synchronize(dev)
+        g_loss = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_loss):
+            loss_step()
+        g_loss.replay()
+        ms_loss, _ = timed_loop(lambda k: g_loss.replay(), 200)
+        loss_info = {"images_per_s": world * BATCH * 200 / (ms_loss / 1e3), "us_per_batch": ms_loss / 200 * 1e3,
+                     "launches_per_batch": 7, "losses": [float(v) for v in losses.tolist()],
+                     "what": "assign (3 launches) + hard-negative mining / loss sums (3) + gradients w.r.t. the predictions (1) "
+                             "for 32 x 640^2 images, synthetic logits, everything resident in HBM; replaces "
+                             "R/nets/retinaface_training.py:183-303 + autograd backward"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import torch_port as tp2
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+            nb = 8
+            cpu_preds = tuple(t[:nb].cpu().clone().requires_grad_(True) for t in (pl, pc, pm))
+            t0 = time.perf_counter()
+            reps = 0
+            while time.perf_counter() - t0 < 6.0 and reps < 10:
+                for q in cpu_preds:
+                    q.grad = None
+                a_, b_, c_ = tp2.multibox_loss(cpu_preds, pri.cpu(), host_sets[0][:nb], THR, list(VAR), 7)
+                (a_ + b_ + c_).backward()
+                reps += 1
+            loss_info["cpu_port_images_per_s"] = nb * reps / (time.perf_counter() - t0)
+            loss_info["cpu_port_sample"] = "%d x the first %d images, oracle/torch_port.multibox_loss forward+backward" % (reps, nb)
+
     # ---- inference side: decode+top-k+NMS at 640^2 (the metric's second half) and at cfg3's 1024^2
     detect_info = None
     if not args.no_extras:
@@ -425,11 +473,34 @@ def main():
             lp, cp, mp = loc_h.pin_memory(), conf_h.pin_memory(), lm_h.pin_memory()
             for _ in range(2):
                 hd(lp, cp, mp)
-            ms_dh, _ = timed_loop(lambda k: hd(lp, cp, mp), n_d)
+            pend_d = []
+
+            def det_e2e(k):                 # two-slot pipeline, drained inside the timed region
+                pend_d.append(hd.submit(lp, cp, mp))
+                if len(pend_d) > 1:
+                    hd.wait(pend_d.pop(0))
+                if k == n_d - 1:
+                    hd.wait(pend_d.pop(0))
+            ms_dh, _ = timed_loop(det_e2e, n_d)
             detect_info[name] = {"images_per_s": world * B * n_d / (ms_d / 1e3), "ms_per_batch": ms_d / n_d,
                                  "e2e_images_per_s": world * B * n_d / (ms_dh / 1e3), "e2e_h2d_bytes": hd.last_h2d,
                                  "e2e_d2h_bytes": hd.last_d2h, "priors": Pd, "batch": B, "mean_kept": float(out[1].float().mean()),
                                  "params": "score>0.02, top-5000, IoU 0.4, keep 750; clustered synthetic predictions"}
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                # the reference's per-image post-processing on the host cores (decode, decode_landm, cat, threshold, top-k,
+                # torchvision NMS; R/predict.py:167-181 composed per SURVEY D4), bounded sample
+                from oracle import torch_port as tp3
+                torch.set_num_threads(len(os.sched_getaffinity(0)))
+                nb = min(B, 4)
+                pr_c = pr.cpu()
+                t0 = time.perf_counter()
+                reps = 0
+                while time.perf_counter() - t0 < 4.0 and reps < 5:
+                    for i in range(nb):
+                        tp3.infer_one_topk(loc_h[i], conf_h[i], lm_h[i], pr_c, list(VAR), 0.02, 5000, 0.4, 750)
+                    reps += 1
+                detect_info[name]["cpu_port_images_per_s"] = nb * reps / (time.perf_counter() - t0)
+                detect_info[name]["cpu_port_sample"] = "%d x the first %d images, oracle/torch_port.infer_one_topk" % (reps, nb)
             # API-form decode (D1): HBM-bound elementwise kernel
             outb = torch.empty_like(loc_d)
             big = [torch.randn((64, Pd, 4), device=dev) * 0.5 for _ in range(4)]
@@ -496,7 +567,7 @@ def main():
                    "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2), one CUDA graph each"
                          % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "phases": phases,
-        "detect": detect_info,
+        "detect": detect_info, "loss": loss_info,
     }
     emit(line)
     return 0

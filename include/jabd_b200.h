@@ -195,6 +195,13 @@ JABD_API int jabd_detect_host(const float *loc_host, const float *conf_host, con
                               int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap, float *dets_host,
                               int *counts_host, int *keep_idx_host, void *dev_scratch, size_t dev_scratch_bytes,
                               jabd_stream_t stream);
+/* Same without the final synchronisation: host buffers must be pinned; the caller waits on `stream` (or an event
+ * recorded on it) before reading the outputs.  Two calls on two streams with two scratch areas overlap. */
+JABD_API int jabd_detect_host_async(const float *loc_host, const float *conf_host, const float *landm_host,
+                              const float *priors_dev, int B, int64_t P, float var0, float var1, float conf_thres,
+                              int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap, float *dets_host,
+                              int *counts_host, int *keep_idx_host, void *dev_scratch, size_t dev_scratch_bytes,
+                              jabd_stream_t stream);
 
 #ifdef __cplusplus
 }

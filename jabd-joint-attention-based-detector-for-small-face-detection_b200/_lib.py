@@ -55,6 +55,8 @@ SIGNATURES = {
     "jabd_detect_host_scratch_bytes": (c_sz, [c_int, c_i64, c_int, c_int]),
     "jabd_detect_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64,
                                  c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_detect_host_async": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64,
+                                       c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
 }
 
 ERRORS = {-1: ValueError, -2: ValueError, -3: ValueError, -4: RuntimeError, -5: RuntimeError}

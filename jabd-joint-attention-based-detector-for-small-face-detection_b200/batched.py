@@ -266,9 +266,11 @@ def assign_targets_host(priors, targets, **kw):
 
 
 class HostDetect(object):
-    """End-to-end host-buffer path (``jabd_detect_host``) for a fixed (B, P, keep_cap) shape."""
+    """End-to-end host-buffer path (``jabd_detect_host``) for a fixed (B, P, keep_cap) shape.  ``h(loc, conf, landm)`` is
+    synchronous; ``submit`` / ``wait`` run the same call as a ``depth``-slot pipeline (``jabd_detect_host_async``, one
+    stream + scratch + pinned output set per slot) so that the next batch's 44 MB upload overlaps this batch's NMS."""
 
-    def __init__(self, priors, B, keep_topk=750, with_landm=True, device=None):
+    def __init__(self, priors, B, keep_topk=750, with_landm=True, device=None, depth=2):
         _tensor.require_cuda()
         self.dev = torch.device(device) if device is not None else _tensor.device_of(priors)
         self.pri = _tensor.to_dev(priors, self.dev)
@@ -276,27 +278,44 @@ class HostDetect(object):
         self.keep_cap = int(keep_topk) if keep_topk and keep_topk > 0 else self.P
         self.with_landm = with_landm
         L = _lib.lib()
-        self.scratch = _tensor.workspace(
-            L.jabd_detect_host_scratch_bytes(self.B, self.P, self.keep_cap, 1 if with_landm else 0), self.dev)
-        self.dets = torch.empty((self.B, self.keep_cap, 15), dtype=torch.float32).pin_memory()
-        self.counts = torch.empty((self.B,), dtype=torch.int32).pin_memory()
-        self.keep_idx = torch.empty((self.B, self.keep_cap), dtype=torch.int32).pin_memory()
+        nbytes = L.jabd_detect_host_scratch_bytes(self.B, self.P, self.keep_cap, 1 if with_landm else 0)
+        self.slots = []
+        for _ in range(max(int(depth), 1)):
+            self.slots.append(dict(scratch=_tensor.workspace(nbytes, self.dev),
+                                   dets=torch.empty((self.B, self.keep_cap, 15), dtype=torch.float32).pin_memory(),
+                                   counts=torch.empty((self.B,), dtype=torch.int32).pin_memory(),
+                                   keep_idx=torch.empty((self.B, self.keep_cap), dtype=torch.int32).pin_memory(),
+                                   stream=torch.cuda.Stream(self.dev), done=torch.cuda.Event()))
+        self.next_slot = 0
+        self.last_h2d = self.B * self.P * 4 * (4 + 2 + (10 if self.with_landm else 0))
+        self.last_d2h = self.B * (self.keep_cap * (60 + 4) + 4)
 
-    def __call__(self, loc, conf, landm, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000,
-                 nms_thres=0.4):
+    def submit(self, loc, conf, landm, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000, nms_thres=0.4):
+        """``loc``/``conf``/``landm``: contiguous CPU f32 tensors (pinned for the copies to overlap).  Returns the slot id."""
         for t, shp in ((loc, (self.B, self.P, 4)), (conf, (self.B, self.P, 2))):
             if t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shp or t.dtype != torch.float32:
                 raise ValueError("HostDetect expects contiguous CPU f32 tensors loc [B,P,4], conf [B,P,2], landm [B,P,10]")
+        k = self.next_slot
+        self.next_slot = (k + 1) % len(self.slots)
+        sl = self.slots[k]
+        sl["done"].synchronize()
         v0, v1 = _tensor.variances_of(variances)
         with torch.cuda.device(self.dev):
-            _lib.call("jabd_detect_host", ptr(loc), ptr(conf), ptr(landm if self.with_landm else None), ptr(self.pri), self.B,
-                      self.P, v0, v1, float(conf_thres), THRESH_GT if strict else THRESH_GE,
-                      int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), self.keep_cap, ptr(self.dets),
-                      ptr(self.counts), ptr(self.keep_idx), ptr(self.scratch), self.scratch.numel(),
-                      _tensor.stream_of(self.dev))
-        self.last_h2d = self.B * self.P * 4 * (4 + 2 + (10 if self.with_landm else 0))
-        self.last_d2h = self.B * (self.keep_cap * (60 + 4) + 4)
-        return self.dets, self.counts, self.keep_idx
+            _lib.call("jabd_detect_host_async", ptr(loc), ptr(conf), ptr(landm if self.with_landm else None), ptr(self.pri),
+                      self.B, self.P, v0, v1, float(conf_thres), THRESH_GT if strict else THRESH_GE,
+                      int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), self.keep_cap, ptr(sl["dets"]),
+                      ptr(sl["counts"]), ptr(sl["keep_idx"]), ptr(sl["scratch"]), sl["scratch"].numel(),
+                      ctypes.c_void_p(sl["stream"].cuda_stream))
+            sl["done"].record(sl["stream"])
+        return k
+
+    def wait(self, slot):
+        sl = self.slots[slot]
+        sl["done"].synchronize()
+        return sl["dets"], sl["counts"], sl["keep_idx"]
+
+    def __call__(self, loc, conf, landm, **kw):
+        return self.wait(self.submit(loc, conf, landm, **kw))
 
 
 def detect_host(loc, conf, landm, priors, **kw):
