@@ -134,6 +134,14 @@ JABD_API int jabd_assign_host(const float *priors_dev, int64_t P, const float *g
                               float *loc_t_host, int64_t *conf_t_host, float *landm_t_host, void *dev_scratch,
                               size_t dev_scratch_bytes, jabd_stream_t stream);
 
+/* ---- box post-processing of Retinaface.detect_image on detection rows [B,K,15], in place:
+ * letterbox != 0: (v - offset) * scale per x / y column (retinaface_correct_boxes, R/utils/utils_bbox.py:9-24);
+ * to_pixels != 0: v * width / height (R/predict.py:194-195).  The score column is untouched.  fp64 arithmetic, one
+ * rounding to fp32 per step, like the reference's numpy code.  post [B,6] doubles (device) =
+ * {offset_x, offset_y, scale_x, scale_y, width, height}; counts [B] (NULL: all K rows of every image). */
+JABD_API int jabd_correct_boxes(float *dets, const int *counts, const double *post, int B, int K, int letterbox,
+                                int to_pixels, jabd_stream_t stream);
+
 /* ---- the rest of MultiBoxLoss.forward (R/nets/retinaface_training.py:229-303) on the assigned
  * targets: positives, hard-negative mining (per-image radix select of the min(negpos_ratio*num_pos, P-1) largest
  * rank values instead of the reference's two full sorts, :270-281), smooth-L1 sums for boxes and landmarks,

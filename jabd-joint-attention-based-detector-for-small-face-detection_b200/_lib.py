@@ -41,6 +41,7 @@ SIGNATURES = {
     "jabd_assign_host_scratch_bytes": (c_sz, [c_int, c_i64, c_i64, c_int]),
     "jabd_assign_host": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_int, c_int, c_int,
                                  c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_correct_boxes": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "jabd_multibox_loss_workspace_bytes": (c_sz, [c_int]),
     "jabd_multibox_loss_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_multibox_loss_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),

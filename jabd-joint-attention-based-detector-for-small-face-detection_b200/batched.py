@@ -17,7 +17,7 @@ import torch
 from . import _lib, _tensor
 from ._tensor import ptr
 
-__all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "detect_host", "multibox_loss"]
+__all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "detect_host", "multibox_loss", "correct_boxes", "letterbox_params"]
 
 THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
 FLAG_DENSE = 1
@@ -136,6 +136,41 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
                   THRESH_GT if strict else THRESH_GE, int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), keep_cap,
                   ptr(dets), ptr(counts), ptr(keep_idx), ptr(ws), ws.numel(), _tensor.stream_of(dev))
     return dets, counts, keep_idx
+
+
+def letterbox_params(input_shape, image_shapes):
+    """Per-image ``[B,6]`` float64 rows {offset_x, offset_y, scale_x, scale_y, width, height} for ``correct_boxes``:
+    the quantities ``retinaface_correct_boxes`` derives from ``input_shape = (H_in, W_in)`` and each image's
+    ``(H, W)`` (R/utils/utils_bbox.py:9-13) plus the pixel scale of R/predict.py:130-137, computed with the same numpy
+    float64 expressions."""
+    inp = np.array(input_shape, dtype=np.float64)
+    rows = []
+    for shp in image_shapes:
+        img = np.array(shp, dtype=np.float64)
+        new_shape = img * np.min(inp / img)
+        offset = (inp - new_shape) / 2. / inp
+        scale = inp / new_shape
+        rows.append([offset[1], offset[0], scale[1], scale[0], float(int(shp[1])), float(int(shp[0]))])
+    return np.array(rows, dtype=np.float64).reshape(-1, 6)
+
+
+def correct_boxes(dets, counts, post, letterbox=True, to_pixels=True):
+    """In-place post-processing of detection rows ``dets [B,K,15]`` (CUDA): undo the letterbox
+    (R/utils/utils_bbox.py:9-24) and / or scale to pixels (R/predict.py:194-195).  ``post``: ``letterbox_params``."""
+    if not (dets.is_cuda and dets.is_contiguous() and dets.dtype == torch.float32 and dets.ndim == 3 and dets.shape[2] == 15):
+        raise ValueError("dets must be a contiguous CUDA f32 tensor [B, K, 15]")
+    dev = dets.device
+    B, K = int(dets.shape[0]), int(dets.shape[1])
+    p = torch.as_tensor(np.ascontiguousarray(post, dtype=np.float64)).to(dev) if not isinstance(post, torch.Tensor) else post
+    if tuple(p.shape) != (B, 6) or p.dtype != torch.float64 or not p.is_cuda:
+        raise ValueError("post must be [B, 6] float64 (see letterbox_params)")
+    cnt = None
+    if counts is not None:
+        cnt = counts.to(dev, torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        _lib.call("jabd_correct_boxes", ptr(dets), ptr(cnt), ptr(p.contiguous()), B, K, 1 if letterbox else 0,
+                  1 if to_pixels else 0, _tensor.stream_of(dev))
+    return dets
 
 
 class _MultiBoxLossFn(torch.autograd.Function):

@@ -159,6 +159,31 @@ __global__ void __launch_bounds__(256) decode_kernel(const float4 *__restrict__ 
         if (b0 + k < batch) __stcs(out + (long long)(b0 + k) * P + p, decode_box(l[k], pr, var0, var1));
 }
 
+// Box post-processing of Retinaface.detect_image on the kept rows: undo the letterbox padding
+// (retinaface_correct_boxes, R/utils/utils_bbox.py:9-24) and scale to pixels (R/predict.py:194-195).  The reference does
+// both in numpy: float32 rows op float64 vectors -> float64, stored back to float32 -- so every step here is evaluated in
+// fp64 and rounded to fp32 once per step.  post[b] = {offset_x, offset_y, scale_x, scale_y, width, height}.
+__global__ void __launch_bounds__(256) correct_boxes_kernel(float *__restrict__ dets, const int *__restrict__ counts,
+                                                            const double *__restrict__ post, int B, int K, int letterbox,
+                                                            int to_pixels)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (long long)B * K) return;
+    const int b = (int)(row / K), k = (int)(row % K);
+    if (counts && k >= counts[b]) return;
+    const double *q = post + 6 * b;
+    float *r = dets + row * JABD_DET_ROW;
+#pragma unroll
+    for (int c = 0; c < JABD_DET_ROW; ++c) {
+        if (c == 4) continue; // score
+        const int xy = (c < 4 ? c : c - 5) & 1; // 0: x column, 1: y column
+        float v = r[c];
+        if (letterbox) v = (float)(((double)v - q[xy]) * q[2 + xy]);
+        if (to_pixels) v = (float)((double)v * q[4 + xy]);
+        r[c] = v;
+    }
+}
+
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 } // namespace jabd
@@ -275,6 +300,19 @@ int jabd_encode_landm(const float *matched, const float *priors, int64_t n, floa
 int jabd_decode_landm(const float *pre, const float *priors, int64_t P, int batch, float var0, float *out, jabd_stream_t stream)
 {
     return landm_common("decode_landm", false, pre, priors, P, batch, var0, out, stream);
+}
+
+int jabd_correct_boxes(float *dets, const int *counts, const double *post, int B, int K, int letterbox, int to_pixels,
+                       jabd_stream_t stream)
+{
+    JABD_REQUIRE(B >= 0 && K >= 0, JABD_EINVAL, "correct_boxes: negative size");
+    if (B == 0 || K == 0 || (!letterbox && !to_pixels)) return JABD_OK;
+    JABD_REQUIRE(dets && post, JABD_EINVAL, "correct_boxes: null pointer");
+    JABD_REQUIRE(aligned_to(post, 8) && aligned_to(dets, 4), JABD_EALIGN, "correct_boxes: post must be 8-byte aligned");
+    correct_boxes_kernel<<<blocks_for((long long)B * K, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dets, counts, post, B, K,
+                                                                                                        letterbox, to_pixels);
+    JABD_LAUNCH_CHECK("correct_boxes_kernel");
+    return JABD_OK;
 }
 
 int jabd_decode(const float *loc, const float *priors, int64_t P, int batch, float var0, float var1, float *out,

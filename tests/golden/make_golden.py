@@ -438,6 +438,27 @@ def gen_loss(R):
     save("loss.npz", **out)
 
 
+# ----------------------------------------------------------------------------- box post-processing
+POST_SHAPES = [(480, 640), (1080, 1920), (333, 517), (640, 640), (1200, 800)]
+
+
+def gen_post(R):
+    """retinaface_correct_boxes (R/utils/utils_bbox.py:9-24) followed by the pixel scaling of R/predict.py:194-195."""
+    r_utils_bbox = R[3]
+    rng = np.random.default_rng(1234)
+    out = {}
+    for i, (h, w) in enumerate(POST_SHAPES):
+        x = rng.random((23, 15)).astype(np.float32)
+        y = r_utils_bbox.retinaface_correct_boxes(x.copy(), np.array([640, 640]), np.array([h, w]))
+        scale = [w, h, w, h]
+        scale_for_landmarks = [w, h] * 5
+        z = y.copy()
+        z[:, :4] = z[:, :4] * scale
+        z[:, 5:] = z[:, 5:] * scale_for_landmarks
+        out["in_%d" % i], out["letterbox_%d" % i], out["pixels_%d" % i] = x, y, z
+    save("post.npz", **out)
+
+
 def main():
     R = import_reference()
     gen_priors(R)
@@ -446,6 +467,7 @@ def main():
     gen_nms(R)
     gen_pipeline(R)
     gen_loss(R)
+    gen_post(R)
     if "--check" in sys.argv:
         sys.exit(1 if check(R) else 0)
 

@@ -236,3 +236,35 @@ def test_detect_cfg3_batch_vs_oracle(mods, gen):
     c = int(c2[0])
     assert c == len(e_i) and np.array_equal(k2[0, :c].cpu().numpy(), e_i)
     assert np.array_equal(d2[0, :c, :5].cpu().numpy(), e_d[:, :5]) and (d2[0, :c, 5:] == 0).all()
+
+
+def test_correct_boxes_matches_reference_numpy(mods):
+    """letterbox undo + pixel scaling on kept rows == the reference's numpy code
+    (retinaface_correct_boxes R/utils/utils_bbox.py:9-24 via the host-side drop-in restatement, then
+    R/predict.py:194-195), bit for bit, for ragged counts and non-square images."""
+    from jabd_b200 import batched, utils_bbox
+    g = torch.Generator().manual_seed(11)
+    B, K = 5, 37
+    dets = torch.rand((B, K, 15), generator=g, dtype=torch.float32)
+    counts = torch.tensor([37, 0, 5, 20, 1], dtype=torch.int32)
+    input_shape = (640, 640)
+    shapes = [(480, 640), (1080, 1920), (333, 517), (640, 640), (1200, 800)]
+    post = batched.letterbox_params(input_shape, shapes)
+    out = batched.correct_boxes(dets.clone().cuda(), counts.cuda(), post).cpu().numpy()
+    for b in range(B):
+        c = int(counts[b])
+        ref = dets[b, :c].numpy().copy()
+        if c:
+            ref = utils_bbox.retinaface_correct_boxes(ref, np.array(input_shape), np.array(shapes[b]))
+            h, w = shapes[b]
+            ref[:, :4] = ref[:, :4] * [w, h, w, h]
+            ref[:, 5:] = ref[:, 5:] * ([w, h] * 5)
+        assert np.array_equal(out[b, :c], ref)
+        assert np.array_equal(out[b, c:], dets[b, c:].numpy())       # rows past the count are untouched
+    only_px = batched.correct_boxes(dets.clone().cuda(), None, post, letterbox=False).cpu().numpy()
+    ref = dets.numpy().copy()
+    for b in range(B):
+        h, w = shapes[b]
+        ref[b, :, :4] = ref[b, :, :4] * [w, h, w, h]
+        ref[b, :, 5:] = ref[b, :, 5:] * ([w, h] * 5)
+    assert np.array_equal(only_px, ref)

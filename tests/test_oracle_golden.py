@@ -245,3 +245,26 @@ def test_multibox_loss_torch_port(tag, size, batch, count):
     else:
         np.testing.assert_array_equal(sha(g_loc), g[tag + "_g_loc_sha"])
         np.testing.assert_array_equal(g_conf.reshape(-1, 2)[g[tag + "_g_conf_nz_idx"]], g[tag + "_g_conf_nz"])
+
+
+def test_correct_boxes_host_restatement():
+    """the host-side drop-in of retinaface_correct_boxes (R/utils/utils_bbox.py:9-24) and the
+    letterbox_params used by the CUDA kernel reproduce the reference's outputs bit for bit."""
+    from jabd_b200 import batched, utils_bbox
+    g = load_golden("post.npz")
+    shapes = [(480, 640), (1080, 1920), (333, 517), (640, 640), (1200, 800)]
+    post = batched.letterbox_params((640, 640), shapes)
+    for i, (h, w) in enumerate(shapes):
+        x = g["in_%d" % i]
+        y = utils_bbox.retinaface_correct_boxes(x.copy(), np.array([640, 640]), np.array([h, w]))
+        np.testing.assert_array_equal(y, g["letterbox_%d" % i])
+        # the same arithmetic from the [B,6] parameter rows (what correct_boxes_kernel evaluates in fp64)
+        q = post[i]
+        z = x.copy()
+        for c in range(15):
+            if c == 4:
+                continue
+            xy = (c if c < 4 else c - 5) & 1
+            z[:, c] = ((z[:, c].astype(np.float64) - q[xy]) * q[2 + xy]).astype(np.float32)
+            z[:, c] = (z[:, c].astype(np.float64) * q[4 + xy]).astype(np.float32)
+        np.testing.assert_array_equal(z, g["pixels_%d" % i])
