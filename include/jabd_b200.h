@@ -168,7 +168,11 @@ JABD_API int jabd_multibox_loss_backward(const float *loc_data, const float *con
  *               order, suppress iff (double)(inter/((area_i+area_j)-inter)) > nms_thres;
  *           1 = SSD-legacy nms / nms_r (R/utils/box_utils.py:384-448, R/utils/utils_bbox.py:116-180): ascending
  *               order picked from the end (ties: higher index first), union = (area_j-inter)+area_i,
- *               survive iff IoU <= (float)nms_thres.                                                  */
+ *               survive iff IoU <= (float)nms_thres.
+ *           | JABD_NMS_EXACT_DIV: evaluate inter/union for every pair.  By default a pair whose IoU is more
+ *               than 2^-20 (relative) away from the threshold is decided by comparing inter with thr*union,
+ *               which provably gives the same decision (detect.cu, suppresses()); tests compare the two. */
+#define JABD_NMS_EXACT_DIV 256
 
 /* Segmented top-k (K1; stable descending order, ties -> lower index).  scores[s*seg_stride + i*elem_stride],
  * i < N, for s < S segments; out_idx [S,K] i32 (padding -1), out_count [S]. */

@@ -64,6 +64,7 @@ def test_topk_segmented(mods):
     s = (rng.integers(0, 50, size=(5, 20000)) / 50.0).astype(np.float32)
     s[3] = 0.25                       # one segment where every score ties
     s[4, ::3] = -s[4, ::3]            # negative scores order correctly
+    s[2] = (0.5 + 0.06 * rng.random(20000)).astype(np.float32)   # all in one 11-bit bin: the refinement passes run
     for k, thr in ((1, None), (100, None), (5000, 0.5), (7000, None), (6144, None), (20000, None), (20000, 0.9)):
         idx, cnt = ops.topk(cuda(s), k, conf_thres=thr, strict=True)
         idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
@@ -268,3 +269,65 @@ def test_correct_boxes_matches_reference_numpy(mods):
         ref[b, :, :4] = ref[b, :, :4] * [w, h, w, h]
         ref[b, :, 5:] = ref[b, :, 5:] * ([w, h] * 5)
     assert np.array_equal(only_px, ref)
+
+
+def _adversarial_boxes(rng, n, nonfinite):
+    """Mixed-size boxes over (and beyond) the unit square with the inputs the kept index must route around:
+    huge boxes, zero-area and negative-side boxes, exact duplicates, far out-of-range and (optionally) non-finite
+    coordinates."""
+    c = rng.random((n, 2), dtype=np.float32) * 1.2 - 0.1
+    scale = np.exp(rng.uniform(np.log(0.003), np.log(0.6), size=(n, 1))).astype(np.float32)
+    wh = scale * (0.6 + 0.8 * rng.random((n, 2), dtype=np.float32))
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    idx = rng.permutation(n)
+    b[idx[:20], 2:] = b[idx[:20], :2]                              # zero area
+    b[idx[20:30], 2] = b[idx[20:30], 0] - 0.01                      # negative width
+    b[idx[30:60]] = b[idx[60:90]]                                   # exact duplicates
+    b[idx[90:95]] *= 1000.0                                         # far out of the grid's coordinate bound
+    b[idx[101:140]] = np.array([0.0, 0.0, 1.0, 1.0], np.float32) + 0.01 * rng.standard_normal((39, 4)).astype(np.float32)
+    # pairs whose IoU is exactly 0.5 / 0.25 / within a few ulp of 0.3: the sliver where the quotient is evaluated
+    b[idx[140:150]] = [0.25, 0.25, 0.5, 0.5]
+    b[idx[150:160]] = [0.25, 0.25, 0.5, 0.375]
+    b[idx[160:170]] = [0.25, 0.25, 0.3125, 0.5]
+    b[idx[170:180]] = np.float32([0.6, 0.6, 0.7, 0.7])
+    b[idx[180:190]] = np.float32([0.6, 0.6, 0.7, 0.63])
+    b[idx[180:190], 3] += (np.arange(10, dtype=np.float32) - 5) * np.float32(6e-8)
+    if nonfinite:
+        b[idx[95:97], 0] = np.nan
+        b[idx[97:99], 3] = np.inf
+        b[idx[99:101]] = [-np.inf, 0.1, 0.5, 0.5]
+    s = rng.random(n, dtype=np.float32)
+    s[::5] = s[2]
+    return b, s
+
+
+@pytest.mark.parametrize("n", [700, 5000, 9000])
+def test_nms_division_free_decision_equals_exact_and_oracle(mods, n):
+    """suppresses() (detect.cu) decides most pairs by comparing inter with thr*union instead of dividing; that never
+    changes a decision: default == JABD_NMS_EXACT_DIV == oracle for torchvision and SSD semantics, thresholds 0 / 0.3 /
+    0.5 and a negative one, on mixed-size boxes with zero-area, negative-side, duplicate, far-away boxes and pairs whose
+    IoU sits exactly on / within ulps of the threshold.  With non-finite coordinates (which the reference never
+    produces) the two paths must still agree with each other."""
+    ops, orc = mods["ops"], mods["orc"]
+    dev = torch.device("cuda", 0)
+    DENSE = 256   # JABD_NMS_EXACT_DIV
+    for nonfinite in (False, True):
+        b, s = _adversarial_boxes(np.random.default_rng(100 + n), n, nonfinite)
+        cb, cs = cuda(b), cuda(s)
+        for thr in (0.0, 0.3, 0.5, -0.25):
+            out = []
+            for mode in (ops.NMS_TV, ops.NMS_TV | DENSE):
+                keep, cnt = ops.nms_indices(cb, 4, cs, 1, n, 0.0, ops.THRESH_NONE, 0, thr, mode, n, dev)
+                out.append(keep[:int(cnt.item())].cpu().numpy())
+            assert np.array_equal(out[0], out[1]), (thr, nonfinite)
+            if not nonfinite:
+                assert np.array_equal(out[0], orc.nms_tv(b, s, thr)), thr
+        for (ov, tk) in ((0.5, 200), (0.3, n), (0.0, n)):
+            out = []
+            for mode in (ops.NMS_SSD, ops.NMS_SSD | DENSE):
+                keep, cnt = ops.nms_indices(cb, 4, cs, 1, n, 0.0, ops.THRESH_NONE, tk, ov, mode, min(n, tk), dev)
+                out.append(keep[:int(cnt.item())].cpu().numpy())
+            assert np.array_equal(out[0], out[1]), (ov, tk, nonfinite)
+            if not nonfinite:
+                rk, rc = orc.nms_ssd(b, s, ov, tk)
+                assert np.array_equal(out[0], rk[:rc]), (ov, tk)
