@@ -162,6 +162,30 @@ JABD_API int jabd_multibox_loss_backward(const float *loc_data, const float *con
                                          const float *norms, const float *grad_losses, int B, int64_t P, float *g_loc,
                                          float *g_conf, float *g_landm, jabd_stream_t stream);
 
+/* ---- WIDER-FACE AP evaluation (R/utils/utils_map.py:75-223), fp64 like the reference.
+ * Rows: pred [sumN,5] = x y w h score per detection in file order (read_pred_file, :45-58), gt [sumG,4] = x y w h,
+ * packed per image with pred_off / gt_off [I+1]; keep [sumG] u8 = 1 for the faces listed in the subset's gt_list
+ * (`ignore[keep_index-1] = 1`, :198-200).
+ * jabd_norm_score: in-place min-max normalisation of all scores (norm_score, :75-98; min starts at 1, max at 0).
+ * jabd_wider_eval: per image image_eval (:100-132) + img_pr_info (:135-148), added into pr_curve [thresh_num,2]
+ *   (the `pr_curve += _img_pr_info` of evaluation, :203); images with no predictions or no GT are skipped (:196-197).
+ *   Optional per-prediction outputs of image_eval: pred_recall [sumN] i32, proposal_list [sumN] i32 (+1 / -1); rows of
+ *   skipped images are left untouched (pred_recall) / set to 1 (proposal_list).
+ * dataset_pr_info and voc_ap (:151-170) are 1000-element host arithmetic and stay in the Python drop-in. */
+/* bbox_overlaps (:16-27) on point-form fp64 boxes [A,4] x [B,4] -> out [A,B]; img_pr_info (:135-148) for one image from
+ * image_eval's outputs: pred [N,5], proposal_list [N] i32 (+1/-1), pred_recall [N] i32 -> pr_info [thresh_num,2] (overwritten);
+ * workspace: 256-byte aligned, >= round_up(4*thresh_num,256) + round_up(4*N,256) bytes. */
+JABD_API int jabd_bbox_overlaps_f64(const double *box_a, int64_t A, const double *box_b, int64_t B, double *out,
+                                    jabd_stream_t stream);
+JABD_API int jabd_img_pr_info(const double *pred, int64_t N, const int *proposal_list, const int *pred_recall,
+                              int thresh_num, double *pr_info, void *workspace, size_t workspace_bytes, jabd_stream_t stream);
+JABD_API int jabd_norm_score(double *pred, int64_t sumN, void *workspace, size_t workspace_bytes, jabd_stream_t stream);
+JABD_API size_t jabd_wider_eval_workspace_bytes(int I, int64_t sumN, int64_t sumG, int thresh_num);
+JABD_API int jabd_wider_eval(const double *pred, const int *pred_off, const double *gt, const int *gt_off,
+                             const unsigned char *keep, int I, int64_t sumN, int64_t sumG, double iou_thresh,
+                             int thresh_num, double *pr_curve, int *pred_recall, int *proposal_list, void *workspace,
+                             size_t workspace_bytes, jabd_stream_t stream);
+
 /* ---- S1/K1/N1/N2: score threshold, top-k, greedy NMS ---------------------------------------------- */
 /* thresh_mode: 0 = none, 1 = score >= conf_thres (R/utils/utils_bbox.py:266), 2 = score > conf_thres. */
 /* nms_mode: 0 = torchvision.ops.nms semantics (call site R/utils/utils_bbox.py:275-279): stable descending

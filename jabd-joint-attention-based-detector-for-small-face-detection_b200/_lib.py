@@ -45,6 +45,11 @@ SIGNATURES = {
     "jabd_multibox_loss_workspace_bytes": (c_sz, [c_int]),
     "jabd_multibox_loss_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_multibox_loss_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "jabd_bbox_overlaps_f64": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "jabd_img_pr_info": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_norm_score": (c_int, [c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "jabd_wider_eval_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_int]),
+    "jabd_wider_eval": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_f64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_topk_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
     "jabd_topk": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_nms_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),

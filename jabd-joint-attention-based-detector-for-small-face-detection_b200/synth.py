@@ -14,7 +14,7 @@ import torch
 
 __all__ = [
     "gt_count", "make_gt", "make_gt_batch", "pack_gt", "make_preds_random",
-    "make_preds_clustered", "dense_iou_for_synthesis",
+    "make_preds_clustered", "dense_iou_for_synthesis", "make_eval_image",
 ]
 
 
@@ -152,3 +152,39 @@ def make_preds_clustered(cfg_id, image_idx, priors, gt, variances=(0.1, 0.2), de
     s = torch.where(near, s_hi, s)
     conf = torch.stack([1.0 - s, s], 1).contiguous()
     return loc.contiguous(), conf, landm.contiguous()
+
+
+def make_eval_image(cfg_id, image_idx, image_size=(640, 640), count=None, max_dets=750):
+    """One image of a WIDER-style evaluation set, in the units of R/utils/utils_map.py: ``gt [G,4]`` float64 pixels
+    (x y w h), ``keeps`` = three uint8 flag arrays (easy: side >= 32 px, medium: >= 16 px, hard: all -- nested like
+    the WIDER subsets) and ``pred [N,5]`` float64 (x y w h score) sorted by descending score: jittered copies of most
+    GT (some twice, so a GT is hit by several predictions), plus random false positives; a few images come out with no
+    predictions or no GT."""
+    import numpy as np
+    H, W = int(image_size[0]), int(image_size[1])
+    rng = np.random.default_rng(7000 * int(cfg_id) + int(image_idx))
+    kind = int(image_idx) % 11
+    G = 0 if kind == 7 else (int(count) if count is not None else int(1 + rng.integers(0, 60)))
+    side = np.exp(rng.uniform(np.log(6.0), np.log(120.0), G))
+    w, h = np.round(side), np.round(side * rng.uniform(1.0, 1.4, G))
+    x, y = np.floor(rng.uniform(0, W - w)), np.floor(rng.uniform(0, H - h))
+    gt = np.stack([x, y, w, h], 1).astype(np.float64).reshape(-1, 4)
+    hard = np.ones(G, np.uint8)
+    keeps = [(np.minimum(w, h) >= 32).astype(np.uint8), (np.minimum(w, h) >= 16).astype(np.uint8), hard]
+    rows = []
+    for g in range(G):
+        for _ in range(int(rng.integers(0, 3))):
+            j = rng.normal(0.0, 0.08, 4) * np.array([w[g], h[g], w[g], h[g]])
+            rows.append([x[g] + j[0], y[g] + j[1], max(w[g] + j[2], 1.0), max(h[g] + j[3], 1.0), rng.uniform(0.3, 1.0)])
+    for _ in range(int(rng.integers(0, 40))):
+        s2 = np.exp(rng.uniform(np.log(6.0), np.log(120.0)))
+        rows.append([rng.uniform(0, W - s2), rng.uniform(0, H - s2), s2, s2 * rng.uniform(1.0, 1.4), rng.uniform(0.02, 0.6)])
+    pred = np.array(rows, dtype=np.float64).reshape(-1, 5)
+    if kind == 3:
+        pred = pred[:0]
+    pred[:, :4] = np.round(pred[:, :4], 1)            # what a "%.1f" txt writer would leave
+    pred[:, 4] = np.round(pred[:, 4], 8)
+    if pred.shape[0] > 2 and kind == 5:
+        pred[1, 4] = pred[0, 4]                        # tied scores
+    pred = pred[np.argsort(-pred[:, 4], kind="stable")][:max_dets]
+    return gt, keeps, pred

@@ -459,6 +459,57 @@ def gen_post(R):
     save("post.npz", **out)
 
 
+# ----------------------------------------------------------------------------- WIDER AP evaluation
+EVAL_IMAGES = 24
+
+
+def gen_wider_eval(R):
+    """image_eval / img_pr_info / norm_score / dataset_pr_info / voc_ap of R/utils/utils_map.py on a seeded synthetic
+    evaluation set (synth.make_eval_image), composed exactly like evaluation() (:181-211)."""
+    sys.path.insert(0, REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import utils.utils_map as r_map
+    sys.path.remove(REF)
+    imgs = [synth.make_eval_image(6, i) for i in range(EVAL_IMAGES)]
+    pred = {"ev": {str(i): imgs[i][2].copy() for i in range(EVAL_IMAGES)}}
+    r_map.norm_score(pred)
+    out = {"n_images": np.array(EVAL_IMAGES)}
+    thresh_num = 1000
+    for i in range(EVAL_IMAGES):
+        out["norm_%d" % i] = pred["ev"][str(i)]
+    box = np.array([[0., 0., 10., 10.], [5., 5., 15., 20.], [0., 0., 0., 0.], [3., 3., 4., 9.]])
+    out["overlaps_in"] = box
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out["overlaps"] = r_map.bbox_overlaps(box, box[::-1].copy())
+    for s, name in enumerate(("easy", "medium", "hard")):
+        pr_curve = np.zeros((thresh_num, 2))
+        count_face = 0
+        for i in range(EVAL_IMAGES):
+            gt, keeps, _ = imgs[i]
+            p = pred["ev"][str(i)]
+            keep_index = np.nonzero(keeps[s])[0] + 1           # 1-based like the .mat gt_list
+            count_face += len(keep_index)
+            if len(gt) == 0 or len(p) == 0:
+                continue
+            ignore = np.zeros(gt.shape[0])
+            if len(keep_index) != 0:
+                ignore[keep_index - 1] = 1
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rec, prop = r_map.image_eval(p, gt, ignore, 0.4)
+            info = r_map.img_pr_info(thresh_num, p, prop, rec)
+            if s == 2:
+                out["recall_%d" % i], out["proposal_%d" % i] = rec, prop
+                if i < 4:
+                    out["pr_info_%d" % i] = info
+            pr_curve += info
+        out["pr_curve_" + name] = pr_curve
+        out["count_face_" + name] = np.array(count_face)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pc = r_map.dataset_pr_info(thresh_num, pr_curve, count_face)
+        out["ap_" + name] = np.array(r_map.voc_ap(pc[:, 1], pc[:, 0]))
+    save("wider_eval.npz", **out)
+
+
 def main():
     R = import_reference()
     gen_priors(R)
@@ -468,6 +519,7 @@ def main():
     gen_pipeline(R)
     gen_loss(R)
     gen_post(R)
+    gen_wider_eval(R)
     if "--check" in sys.argv:
         sys.exit(1 if check(R) else 0)
 

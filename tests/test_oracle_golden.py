@@ -268,3 +268,30 @@ def test_correct_boxes_host_restatement():
             z[:, c] = ((z[:, c].astype(np.float64) - q[xy]) * q[2 + xy]).astype(np.float32)
             z[:, c] = (z[:, c].astype(np.float64) * q[4 + xy]).astype(np.float32)
         np.testing.assert_array_equal(z, g["pixels_%d" % i])
+
+
+def test_wider_eval_oracle_matches_reference():
+    """oracle/wider_eval.py reproduces the reference's utils_map.py (image_eval, img_pr_info,
+    norm_score, dataset_pr_info + voc_ap) on the seeded synthetic evaluation set, exactly (fp64, integer counters)."""
+    from jabd_b200 import synth
+    from oracle import wider_eval as ow
+    g = load_golden("wider_eval.npz")
+    n = int(g["n_images"])
+    imgs = [synth.make_eval_image(6, i) for i in range(n)]
+    normed = ow.norm_scores([im[2] for im in imgs])
+    for i in range(n):
+        np.testing.assert_array_equal(normed[i], g["norm_%d" % i])
+    np.testing.assert_array_equal(ow.bbox_overlaps(g["overlaps_in"], g["overlaps_in"][::-1]), g["overlaps"])
+    for i in range(n):
+        gt, keeps, _ = imgs[i]
+        if len(gt) == 0 or len(normed[i]) == 0:
+            continue
+        rec, prop = ow.image_eval(normed[i], gt, keeps[2], 0.4)
+        np.testing.assert_array_equal(rec, g["recall_%d" % i])
+        np.testing.assert_array_equal(prop, g["proposal_%d" % i])
+        if i < 4:
+            np.testing.assert_array_equal(ow.img_pr_info(1000, normed[i], prop, rec), g["pr_info_%d" % i])
+    for s, name in enumerate(("easy", "medium", "hard")):
+        pr = ow.pr_counters(normed, [im[0] for im in imgs], [im[1][s] for im in imgs], 0.4, 1000)
+        np.testing.assert_array_equal(pr, g["pr_curve_" + name])
+        assert ow.average_precision(pr, int(g["count_face_" + name])) == float(g["ap_" + name])
