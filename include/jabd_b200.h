@@ -162,6 +162,34 @@ JABD_API int jabd_multibox_loss_backward(const float *loc_data, const float *con
                                          const float *norms, const float *grad_losses, int B, int64_t P, float *g_loc,
                                          float *g_conf, float *g_landm, jabd_stream_t stream);
 
+/* ---- IoU-family overlaps, IouLoss and the DIoU variant of the MultiBox loss.
+ * kind: 1 = IoU, 2 = GIoU, 3 = DIoU, 4 = CIoU.
+ * jabd_bbox_overlaps_family: bbox_overlaps_{iou,giou,diou,ciou}(bboxes1, bboxes2) of R/utils/box_utils.py:5-158 -- the
+ *   reference pairs row i of bboxes1 with row i of bboxes2 -> out [N] (clamped like the reference).
+ * jabd_iou_loss_forward / _backward: IouLoss.forward (R/nets/retinaface_training_DIOU.py:491-525) and its gradient with
+ *   respect to loc_p.  priors != NULL: pred_mode 'Center' (loc_p is decoded against priors [N,4] first), NULL: loc_p are
+ *   boxes.  size_sum != 0: sum, else mean.  per_row [N] (optional) receives 1 - overlap; loss [1], grad_loss [1] device.
+ * jabd_multibox_loss_forward_ex / _backward_ex: jabd_multibox_loss_* with the box term selected by loc_loss: 0 =
+ *   smooth-L1 on encoded targets, 1..4 = IouLoss(kind) on decode(loc_data, priors [P,4]) against raw matched boxes in
+ *   loc_t (jabd_assign with encode_mode 0, i.e. match_iou) -- MultiBoxLoss of R/nets/retinaface_training_DIOU.py:527-665. */
+JABD_API int jabd_bbox_overlaps_family(const float *boxes1, const float *boxes2, int64_t N, int kind, float *out,
+                                       jabd_stream_t stream);
+JABD_API int jabd_iou_loss_forward(const float *loc_p, const float *loc_t, const float *priors, int64_t N, float var0,
+                                   float var1, int kind, int size_sum, float *per_row, float *loss, jabd_stream_t stream);
+JABD_API int jabd_iou_loss_backward(const float *loc_p, const float *loc_t, const float *priors, int64_t N, float var0,
+                                    float var1, int kind, int size_sum, const float *grad_loss, float *g_loc,
+                                    jabd_stream_t stream);
+JABD_API int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data, const float *landm_data,
+                                           const float *loc_t, const int64_t *conf_t, const float *landm_t, int B, int64_t P,
+                                           int negpos_ratio, int loc_loss, const float *priors, float var0, float var1,
+                                           float *losses, float *norms, unsigned char *sel_mask, void *workspace,
+                                           size_t workspace_bytes, jabd_stream_t stream);
+JABD_API int jabd_multibox_loss_backward_ex(const float *loc_data, const float *conf_data, const float *landm_data,
+                                            const float *loc_t, const float *landm_t, const unsigned char *sel_mask,
+                                            const float *norms, const float *grad_losses, int B, int64_t P, int loc_loss,
+                                            const float *priors, float var0, float var1, float *g_loc, float *g_conf,
+                                            float *g_landm, jabd_stream_t stream);
+
 /* ---- WIDER-FACE AP evaluation (R/utils/utils_map.py:75-223), fp64 like the reference.
  * Rows: pred [sumN,5] = x y w h score per detection in file order (read_pred_file, :45-58), gt [sumG,4] = x y w h,
  * packed per image with pred_off / gt_off [I+1]; keep [sumG] u8 = 1 for the faces listed in the subset's gt_list
@@ -213,6 +241,13 @@ JABD_API int jabd_nms(const float *boxes, int64_t box_seg_stride, int64_t box_st
                       int64_t score_seg_stride, int64_t score_stride, int S, int64_t N, float conf_thres, int thresh_mode,
                       int pre_nms_topk, double nms_thres, int nms_mode, int keep_cap, int *keep_idx, int *keep_count,
                       void *workspace, size_t workspace_bytes, jabd_stream_t stream);
+
+/* diounms (R/utils/utils_bbox.py:182-258): the SSD-legacy loop (ascending order picked from the end, top_k = pre_nms_topk,
+ * union = (area_j-inter)+area_i) with the criterion IoU - (centre distance^2 / enclosing diagonal^2)^beta1 <= overlap. */
+JABD_API int jabd_diounms(const float *boxes, int64_t box_seg_stride, int64_t box_stride, const float *scores,
+                          int64_t score_seg_stride, int64_t score_stride, int S, int64_t N, int pre_nms_topk, double overlap,
+                          float beta1, int keep_cap, int *keep_idx, int *keep_count, void *workspace, size_t workspace_bytes,
+                          jabd_stream_t stream);
 
 /* Fused inference post-processing for a batch (R/predict.py:167-181 composed per SURVEY D4):
  * class-1 score (conf[:,1]) -> threshold -> top-k -> decode of the candidates -> NMS -> first keep_cap rows

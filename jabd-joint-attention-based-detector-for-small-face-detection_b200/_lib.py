@@ -45,6 +45,13 @@ SIGNATURES = {
     "jabd_multibox_loss_workspace_bytes": (c_sz, [c_int]),
     "jabd_multibox_loss_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_multibox_loss_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "jabd_bbox_overlaps_family": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
+    "jabd_iou_loss_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_vp]),
+    "jabd_iou_loss_backward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_int, c_int, c_vp, c_vp, c_vp]),
+    "jabd_multibox_loss_forward_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_f32, c_f32,
+                                              c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_multibox_loss_backward_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_f32,
+                                               c_f32, c_vp, c_vp, c_vp, c_vp]),
     "jabd_bbox_overlaps_f64": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "jabd_img_pr_info": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
     "jabd_norm_score": (c_int, [c_vp, c_i64, c_vp, c_sz, c_vp]),
@@ -55,6 +62,8 @@ SIGNATURES = {
     "jabd_nms_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
     "jabd_nms": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_i64, c_f32, c_int, c_int, c_f64, c_int,
                          c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_diounms": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_i64, c_int, c_f64, c_f32, c_int, c_vp, c_vp, c_vp,
+                             c_sz, c_vp]),
     "jabd_detect_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
     "jabd_detect": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -8,6 +8,7 @@ from ._tensor import ptr
 
 THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
 NMS_TV, NMS_SSD = 0, 1
+IOU, GIOU, DIOU, CIOU = 1, 2, 3, 4
 
 
 def _rows(x, cols, name):
@@ -155,3 +156,36 @@ def topk(scores, k, conf_thres=None, strict=True):
     if squeeze:
         out, cnt = out[0], cnt[0]
     return _tensor.like(kind, out), _tensor.like(kind, cnt)
+
+
+def overlaps_family(bboxes1, bboxes2, kind):
+    """``bbox_overlaps_{iou,giou,diou,ciou}`` (R/utils/box_utils.py:5-158): row i of ``bboxes1`` against row i of
+    ``bboxes2`` (one row broadcasts, like the reference's torch.min / torch.max), result ``[N]`` fp32."""
+    knd, dev = _tensor.kind_of(bboxes1), _tensor.device_of(bboxes1, bboxes2)
+    a, b = _tensor.to_dev(bboxes1, dev).reshape(-1, 4), _tensor.to_dev(bboxes2, dev).reshape(-1, 4)
+    rows, cols = int(a.shape[0]), int(b.shape[0])
+    if rows * cols == 0:
+        return _tensor.like(knd, torch.zeros((rows, cols), dtype=torch.float32, device=dev))   # :9-10
+    if rows > cols:                                                                           # :12-15
+        a, b = b, a
+    if a.shape[0] != b.shape[0]:
+        if a.shape[0] != 1:
+            raise RuntimeError("The size of tensor a (%d) must match the size of tensor b (%d) at non-singleton dimension 0"
+                               % (a.shape[0], b.shape[0]))
+        a = a.expand(b.shape[0], 4).contiguous()
+    out = torch.empty((a.shape[0],), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("jabd_bbox_overlaps_family", ptr(a), ptr(b), a.shape[0], int(kind), ptr(out), _tensor.stream_of(dev))
+    return _tensor.like(knd, out)
+
+
+def diounms_indices(boxes, scores, n, top_k, overlap, beta1, keep_cap, dev):
+    """Single-segment ``jabd_diounms``; returns (keep_idx i32 [keep_cap] CUDA, count i32 [1] CUDA)."""
+    L = _lib.lib()
+    keep = torch.empty((max(keep_cap, 1),), dtype=torch.int32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    ws = _tensor.workspace(L.jabd_nms_workspace_bytes(1, n, keep_cap), dev)
+    with torch.cuda.device(dev):
+        _lib.call("jabd_diounms", ptr(boxes), 0, 4, ptr(scores), 0, 1, 1, n, int(top_k), float(overlap), float(beta1), keep_cap,
+                  ptr(keep), ptr(count), ptr(ws), ws.numel(), _tensor.stream_of(dev))
+    return keep, count

@@ -178,7 +178,8 @@ class _MultiBoxLossFn(torch.autograd.Function):
     (R/nets/retinaface_training.py:229-303) as one autograd node over the network outputs."""
 
     @staticmethod
-    def forward(ctx, loc_data, conf_data, landm_data, loc_t, conf_t, landm_t, negpos_ratio):
+    def forward(ctx, loc_data, conf_data, landm_data, loc_t, conf_t, landm_t, negpos_ratio, loc_loss=0, priors=None, var0=0.1,
+                var1=0.2):
         dev = loc_data.device
         B, P = int(loc_data.shape[0]), int(loc_data.shape[1])
         ld, cd, md = (t.detach().contiguous().float() for t in (loc_data, conf_data, landm_data))
@@ -188,9 +189,11 @@ class _MultiBoxLossFn(torch.autograd.Function):
         L = _lib.lib()
         ws = _tensor.workspace(L.jabd_multibox_loss_workspace_bytes(B), dev)
         with torch.cuda.device(dev):
-            _lib.call("jabd_multibox_loss_forward", ptr(ld), ptr(cd), ptr(md), ptr(loc_t), ptr(conf_t), ptr(landm_t), B, P,
-                      int(negpos_ratio), ptr(losses), ptr(norms), ptr(mask), ptr(ws), ws.numel(), _tensor.stream_of(dev))
+            _lib.call("jabd_multibox_loss_forward_ex", ptr(ld), ptr(cd), ptr(md), ptr(loc_t), ptr(conf_t), ptr(landm_t), B, P,
+                      int(negpos_ratio), int(loc_loss), ptr(priors), float(var0), float(var1), ptr(losses), ptr(norms), ptr(mask),
+                      ptr(ws), ws.numel(), _tensor.stream_of(dev))
         ctx.save_for_backward(ld, cd, md, loc_t, landm_t, mask, norms)
+        ctx.loc_loss, ctx.priors, ctx.var = int(loc_loss), priors, (float(var0), float(var1))
         ctx.mark_non_differentiable(mask, norms)
         return losses[0], losses[1], losses[2], mask, norms
 
@@ -203,16 +206,23 @@ class _MultiBoxLossFn(torch.autograd.Function):
         g = torch.stack([(x if x is not None else zero).to(dev, torch.float32).reshape(()) for x in (g_l, g_c, g_landm)]).contiguous()
         g_loc, g_conf, g_lm = torch.empty_like(ld), torch.empty_like(cd), torch.empty_like(md)
         with torch.cuda.device(dev):
-            _lib.call("jabd_multibox_loss_backward", ptr(ld), ptr(cd), ptr(md), ptr(loc_t), ptr(landm_t), ptr(mask), ptr(norms),
-                      ptr(g), B, P, ptr(g_loc), ptr(g_conf), ptr(g_lm), _tensor.stream_of(dev))
-        return g_loc, g_conf, g_lm, None, None, None, None
+            _lib.call("jabd_multibox_loss_backward_ex", ptr(ld), ptr(cd), ptr(md), ptr(loc_t), ptr(landm_t), ptr(mask), ptr(norms),
+                      ptr(g), B, P, ctx.loc_loss, ptr(ctx.priors), ctx.var[0], ctx.var[1], ptr(g_loc), ptr(g_conf), ptr(g_lm),
+                      _tensor.stream_of(dev))
+        return g_loc, g_conf, g_lm, None, None, None, None, None, None, None, None
 
 
-def multibox_loss(predictions, loc_t, conf_t, landm_t, negpos_ratio=7, return_aux=False):
+LOC_LOSS = {"smooth_l1": 0, "Iou": 1, "Giou": 2, "Diou": 3, "Ciou": 4}
+
+
+def multibox_loss(predictions, loc_t, conf_t, landm_t, negpos_ratio=7, return_aux=False, loc_loss="smooth_l1", priors=None,
+                  variances=(0.1, 0.2)):
     """``(loss_l, loss_c, loss_landm)`` of R/nets/retinaface_training.py:229-303 for CUDA predictions
     ``(loc_data [B,P,4], conf_data [B,P,2] logits, landm_data [B,P,10])`` and the targets of ``assign_targets``.
     Differentiable w.r.t. the predictions.  ``return_aux`` adds the selection mask ``[B,P]`` u8 (bit0 pos, bit1
-    pos1, bit2 mined negative) and ``(N, N1)``."""
+    pos1, bit2 mined negative) and ``(N, N1)``.  ``loc_loss`` "Iou" / "Giou" / "Diou" / "Ciou" replaces the smooth-L1 box
+    term by ``IouLoss`` on ``decode(loc_data, priors)`` against raw matched boxes in ``loc_t`` (``assign_targets(...,
+    encode=False)``), i.e. the MultiBoxLoss of R/nets/retinaface_training_DIOU.py:527-665."""
     loc_data, conf_data, landm_data = predictions
     B, P = int(loc_data.shape[0]), int(loc_data.shape[1])
     if not loc_data.is_cuda:
@@ -222,7 +232,17 @@ def multibox_loss(predictions, loc_t, conf_t, landm_t, negpos_ratio=7, return_au
     for t, shp, dt in ((loc_t, (B, P, 4), torch.float32), (conf_t, (B, P), torch.int64), (landm_t, (B, P, 10), torch.float32)):
         if not (t.is_cuda and t.is_contiguous() and tuple(t.shape) == shp and t.dtype == dt):
             raise ValueError("targets must be the contiguous CUDA tensors returned by assign_targets")
-    l, c, m, mask, norms = _MultiBoxLossFn.apply(loc_data, conf_data, landm_data, loc_t, conf_t, landm_t, int(negpos_ratio))
+    kind = LOC_LOSS[loc_loss] if isinstance(loc_loss, str) else int(loc_loss)
+    pri = None
+    if kind:
+        if priors is None:
+            raise ValueError("the IoU-family box loss decodes loc_data and needs the priors")
+        pri = _tensor.to_dev(priors, loc_data.device)
+        if tuple(pri.shape) != (P, 4):
+            raise ValueError("priors must be [P, 4]")
+    v0, v1 = _tensor.variances_of(variances)
+    l, c, m, mask, norms = _MultiBoxLossFn.apply(loc_data, conf_data, landm_data, loc_t, conf_t, landm_t, int(negpos_ratio), kind,
+                                                 pri, v0, v1)
     return (l, c, m, mask, norms) if return_aux else (l, c, m)
 
 

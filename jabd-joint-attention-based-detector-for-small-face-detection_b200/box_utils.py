@@ -2,13 +2,35 @@
 
 Nobody imports that file in the reference, but its signatures are part of the public surface
 the north star names, so they are kept: 8-argument ``match`` / ``match_ious`` (labels + 1, no landmarks),
-``encode`` / ``decode`` and the pure-torch greedy ``nms`` (ascending sort, ``top_k``, zero-padded keep + count).
+``encode`` / ``decode``, the pure-torch greedy ``nms`` (ascending sort, ``top_k``, zero-padded keep + count) and the
+element-wise ``bbox_overlaps_{iou,giou,diou,ciou}`` (:5-158).
 """
 import torch
 
 from . import _ops, _tensor
 
-__all__ = ["point_form", "intersect", "jaccard", "match", "match_ious", "encode", "decode", "nms"]
+__all__ = ["point_form", "intersect", "jaccard", "match", "match_ious", "encode", "decode", "nms", "bbox_overlaps_iou",
+           "bbox_overlaps_giou", "bbox_overlaps_diou", "bbox_overlaps_ciou"]
+
+
+def bbox_overlaps_iou(bboxes1, bboxes2):
+    """R/utils/box_utils.py:96-119: IoU of row i with row i, clamped to [0, 1]."""
+    return _ops.overlaps_family(bboxes1, bboxes2, _ops.IOU)
+
+
+def bbox_overlaps_giou(bboxes1, bboxes2):
+    """R/utils/box_utils.py:121-158: IoU - (closure - union) / closure, clamped to [-1, 1]."""
+    return _ops.overlaps_family(bboxes1, bboxes2, _ops.GIOU)
+
+
+def bbox_overlaps_diou(bboxes1, bboxes2):
+    """R/utils/box_utils.py:5-46: IoU - centre distance^2 / enclosing diagonal^2, clamped to [-1, 1]."""
+    return _ops.overlaps_family(bboxes1, bboxes2, _ops.DIOU)
+
+
+def bbox_overlaps_ciou(bboxes1, bboxes2):
+    """R/utils/box_utils.py:48-94: DIoU with the aspect-ratio term alpha * v."""
+    return _ops.overlaps_family(bboxes1, bboxes2, _ops.CIOU)
 
 
 def point_form(boxes):

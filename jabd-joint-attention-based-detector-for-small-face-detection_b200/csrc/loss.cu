@@ -18,7 +18,7 @@
 //   mbl_forward_kernel   per image: counts, radix select, selection mask [B,P] (bit0 pos, bit1 pos1, bit2 neg), partial sums
 //   mbl_finalize_kernel  batch sums -> losses[3], norms[2]
 //   mbl_backward_kernel  per prior: gradients of the three losses w.r.t. loc_data / conf_data / landm_data
-#include "common.cuh"
+#include "iou_family.cuh"
 
 namespace jabd {
 
@@ -123,6 +123,12 @@ struct LossFwdArgs {
     int negpos_ratio;
     unsigned char *mask;
     LossWs ws;
+    // box regression term: 0 = smooth-L1 on encoded offsets (R/nets/retinaface_training.py:252), 1..4 = IouLoss of
+    // R/nets/retinaface_training_DIOU.py:491-525 ('Iou' / 'Giou' / 'Diou' / 'Ciou') on decode(loc_data, priors) against the
+    // raw matched boxes that match_iou leaves in loc_t (:590-591)
+    int loc_loss;
+    const float4 *priors;
+    float var0, var1;
 };
 
 __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArgs a)
@@ -245,8 +251,13 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
             }
             if (pos) {
                 const float4 lp = __ldg(a.loc_data + row0 + p), lt = __ldg(a.loc_t + row0 + p);
-                sl = fadd(sl, fadd(fadd(smooth_l1(fsub(lp.x, lt.x)), smooth_l1(fsub(lp.y, lt.y))),
-                                   fadd(smooth_l1(fsub(lp.z, lt.z)), smooth_l1(fsub(lp.w, lt.w)))));
+                if (a.loc_loss == 0) {
+                    sl = fadd(sl, fadd(fadd(smooth_l1(fsub(lp.x, lt.x)), smooth_l1(fsub(lp.y, lt.y))),
+                                       fadd(smooth_l1(fsub(lp.z, lt.z)), smooth_l1(fsub(lp.w, lt.w)))));
+                } else {
+                    const float4 box = decode_box(lp, __ldg(a.priors + p), a.var0, a.var1);
+                    sl = fadd(sl, fsub(1.0f, iou_family<float>(a.loc_loss, box_of(box), box_of(lt))));
+                }
             }
             if (pos1) {
                 const float *mp = a.landm_data + (row0 + p) * 10, *mt = a.landm_t + (row0 + p) * 10;
@@ -309,6 +320,10 @@ struct LossBwdArgs {
     float4 *g_loc;
     float2 *g_conf;
     float *g_landm;
+    int loc_loss;       // see LossFwdArgs
+    const float4 *priors;
+    long long P;
+    float var0, var1;
 };
 
 __global__ void __launch_bounds__(256) mbl_backward_kernel(LossBwdArgs a)
@@ -329,10 +344,15 @@ __global__ void __launch_bounds__(256) mbl_backward_kernel(LossBwdArgs a)
         float2 g2 = make_float2(0.f, 0.f);
         if (m & 1u) {
             const float4 lp = __ldg(a.loc_data + i), lt = __ldg(a.loc_t + i);
-            g4.x = fmul(gl, smooth_l1_grad(fsub(lp.x, lt.x)));
-            g4.y = fmul(gl, smooth_l1_grad(fsub(lp.y, lt.y)));
-            g4.z = fmul(gl, smooth_l1_grad(fsub(lp.z, lt.z)));
-            g4.w = fmul(gl, smooth_l1_grad(fsub(lp.w, lt.w)));
+            if (a.loc_loss == 0) {
+                g4.x = fmul(gl, smooth_l1_grad(fsub(lp.x, lt.x)));
+                g4.y = fmul(gl, smooth_l1_grad(fsub(lp.y, lt.y)));
+                g4.z = fmul(gl, smooth_l1_grad(fsub(lp.z, lt.z)));
+                g4.w = fmul(gl, smooth_l1_grad(fsub(lp.w, lt.w)));
+            } else {
+                const float4 r = iou_loss_grad(a.loc_loss, lp, __ldg(a.priors + i % a.P), lt, a.var0, a.var1);
+                g4 = make_float4(gl * r.x, gl * r.y, gl * r.z, gl * r.w);
+            }
         }
         if (m & 5u) { // softmax - onehot(target), target = pos ? 1 : 0
             const float2 c = __ldg(a.conf_data + i);
@@ -382,11 +402,14 @@ size_t jabd_multibox_loss_workspace_bytes(int B)
     return loss_ws_layout(B, nullptr, nullptr);
 }
 
-int jabd_multibox_loss_forward(const float *loc_data, const float *conf_data, const float *landm_data, const float *loc_t,
-                               const int64_t *conf_t, const float *landm_t, int B, int64_t P, int negpos_ratio, float *losses,
-                               float *norms, unsigned char *sel_mask, void *workspace, size_t workspace_bytes,
-                               jabd_stream_t stream)
+int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data, const float *landm_data, const float *loc_t,
+                                  const int64_t *conf_t, const float *landm_t, int B, int64_t P, int negpos_ratio, int loc_loss,
+                                  const float *priors, float var0, float var1, float *losses, float *norms,
+                                  unsigned char *sel_mask, void *workspace, size_t workspace_bytes, jabd_stream_t stream)
 {
+    JABD_REQUIRE(loc_loss >= 0 && loc_loss <= kCiou, JABD_EINVAL, "multibox_loss: loc_loss must be 0 (smooth-L1) or 1..4 (IoU family)");
+    JABD_REQUIRE(loc_loss == 0 || (priors && aligned_to(priors, 16)), JABD_EINVAL,
+                 "multibox_loss: the IoU-family box loss needs 16-byte aligned priors");
     JABD_REQUIRE(B >= 0 && P >= 0 && negpos_ratio >= 0, JABD_EINVAL, "multibox_loss: negative size");
     JABD_REQUIRE(B <= 65535 && (int64_t)B * P < (1ll << 40), JABD_EINVAL, "multibox_loss: batch too large");
     JABD_REQUIRE(losses && norms, JABD_EINVAL, "multibox_loss: null output pointer");
@@ -417,6 +440,10 @@ int jabd_multibox_loss_forward(const float *loc_data, const float *conf_data, co
         a.negpos_ratio = negpos_ratio;
         a.mask = sel_mask;
         a.ws = ws;
+        a.loc_loss = loc_loss;
+        a.priors = reinterpret_cast<const float4 *>(priors);
+        a.var0 = var0;
+        a.var1 = var1;
         mbl_forward_kernel<<<(unsigned)B, kLossThreads, 0, st>>>(a);
         JABD_LAUNCH_CHECK("mbl_forward_kernel");
     }
@@ -425,11 +452,32 @@ int jabd_multibox_loss_forward(const float *loc_data, const float *conf_data, co
     return JABD_OK;
 }
 
+int jabd_multibox_loss_forward(const float *loc_data, const float *conf_data, const float *landm_data, const float *loc_t,
+                               const int64_t *conf_t, const float *landm_t, int B, int64_t P, int negpos_ratio, float *losses,
+                               float *norms, unsigned char *sel_mask, void *workspace, size_t workspace_bytes,
+                               jabd_stream_t stream)
+{
+    return jabd_multibox_loss_forward_ex(loc_data, conf_data, landm_data, loc_t, conf_t, landm_t, B, P, negpos_ratio, 0, nullptr,
+                                         0.0f, 0.0f, losses, norms, sel_mask, workspace, workspace_bytes, stream);
+}
+
 int jabd_multibox_loss_backward(const float *loc_data, const float *conf_data, const float *landm_data, const float *loc_t,
                                 const float *landm_t, const unsigned char *sel_mask, const float *norms,
                                 const float *grad_losses, int B, int64_t P, float *g_loc, float *g_conf, float *g_landm,
                                 jabd_stream_t stream)
 {
+    return jabd_multibox_loss_backward_ex(loc_data, conf_data, landm_data, loc_t, landm_t, sel_mask, norms, grad_losses, B, P, 0,
+                                          nullptr, 0.0f, 0.0f, g_loc, g_conf, g_landm, stream);
+}
+
+int jabd_multibox_loss_backward_ex(const float *loc_data, const float *conf_data, const float *landm_data, const float *loc_t,
+                                   const float *landm_t, const unsigned char *sel_mask, const float *norms,
+                                   const float *grad_losses, int B, int64_t P, int loc_loss, const float *priors, float var0,
+                                   float var1, float *g_loc, float *g_conf, float *g_landm, jabd_stream_t stream)
+{
+    JABD_REQUIRE(loc_loss >= 0 && loc_loss <= kCiou, JABD_EINVAL, "multibox_loss_backward: loc_loss must be 0..4");
+    JABD_REQUIRE(loc_loss == 0 || (priors && aligned_to(priors, 16)), JABD_EINVAL,
+                 "multibox_loss_backward: the IoU-family box loss needs 16-byte aligned priors");
     JABD_REQUIRE(B >= 0 && P >= 0, JABD_EINVAL, "multibox_loss_backward: negative size");
     if (B == 0 || P == 0) return JABD_OK;
     JABD_REQUIRE(loc_data && conf_data && landm_data && loc_t && landm_t && sel_mask && norms && grad_losses && g_loc && g_conf &&
@@ -449,6 +497,11 @@ int jabd_multibox_loss_backward(const float *loc_data, const float *conf_data, c
     a.g_loc = reinterpret_cast<float4 *>(g_loc);
     a.g_conf = reinterpret_cast<float2 *>(g_conf);
     a.g_landm = g_landm;
+    a.loc_loss = loc_loss;
+    a.priors = reinterpret_cast<const float4 *>(priors);
+    a.P = P;
+    a.var0 = var0;
+    a.var1 = var1;
     mbl_backward_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     JABD_LAUNCH_CHECK("mbl_backward_kernel");
     return JABD_OK;

@@ -9,7 +9,7 @@ import torch
 from . import _ops, _tensor
 from . import box_utils as _box_utils
 
-__all__ = ["decode", "decode_landm", "non_max_suppression", "nms_r", "retinaface_correct_boxes"]
+__all__ = ["decode", "decode_landm", "non_max_suppression", "nms_r", "diounms", "retinaface_correct_boxes"]
 
 
 def decode(loc, priors, variances):
@@ -44,6 +44,23 @@ def non_max_suppression(detection, conf_thres=0.5, nms_thres=0.3):
 def nms_r(boxes, scores, overlap=0.5, top_k=200):
     """R/utils/utils_bbox.py:116-180 (same function as ``box_utils.nms``)."""
     return _box_utils.nms(boxes, scores, overlap, top_k)
+
+
+def diounms(boxes, scores, overlap=0.5, top_k=200, beta1=1.0):
+    """R/utils/utils_bbox.py:182-258: greedy NMS on ``IoU - (d / c) ** beta1 <= overlap`` (DIoU-NMS).  Returns
+    ``(keep, count)`` like the reference; the bare zero ``keep`` tensor when ``boxes`` is empty (:196-198)."""
+    kind, dev = _tensor.kind_of(scores), _tensor.device_of(boxes, scores)
+    b = _tensor.to_dev(boxes, dev)
+    s = _tensor.to_dev(scores, dev).reshape(-1)
+    n = int(s.shape[0])
+    keep = torch.zeros((n,), dtype=torch.int64, device=dev)
+    if b.numel() == 0:
+        return _tensor.like(kind, keep)
+    cap = min(n, int(top_k))
+    k32, cnt = _ops.diounms_indices(b.reshape(n, 4), s, n, int(top_k), float(overlap), float(beta1), cap, dev)
+    count = int(cnt.item())
+    keep[:count] = k32[:count].to(torch.int64)
+    return _tensor.like(kind, keep), count
 
 
 def retinaface_correct_boxes(result, input_shape, image_shape):

@@ -357,6 +357,56 @@ ORC_API int64_t orc_nms_ssd(const float *boxes, const int64_t *order_asc, int64_
     return count;
 }
 
+/* diounms, R/utils/utils_bbox.py:182-258: the loop of orc_nms_ssd with the criterion
+ * inter/union - (d/c)^beta1 <= overlap; d = squared centre distance, c = squared diagonal of the enclosing box.
+ * torch.pow(u, 1.0) returns u itself. */
+ORC_API int64_t orc_diounms(const float *boxes, const int64_t *order_asc, int64_t n, float overlap, int64_t top_k,
+                            float beta1, int64_t *keep)
+{
+    for (int64_t i = 0; i < n; ++i) keep[i] = 0;
+    if (n <= 0) return 0;
+    int64_t m = n < top_k ? n : top_k;
+    int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)m);
+    memcpy(idx, order_asc + (n - m), sizeof(int64_t) * (size_t)m);
+    int64_t count = 0;
+    while (m > 0) {
+        int64_t i = idx[m - 1];
+        keep[count++] = i;
+        if (m == 1) break;
+        --m;
+        const float *bi = boxes + 4 * i;
+        float area_i = (bi[2] - bi[0]) * (bi[3] - bi[1]);
+        float cxi = (bi[0] + bi[2]) / 2, cyi = (bi[1] + bi[3]) / 2;
+        int64_t w_ = 0;
+        for (int64_t k = 0; k < m; ++k) {
+            int64_t j = idx[k];
+            const float *bj = boxes + 4 * j;
+            float inx1 = bj[0] < bi[0] ? bi[0] : bj[0], iny1 = bj[1] < bi[1] ? bi[1] : bj[1];
+            float inx2 = bj[2] > bi[2] ? bi[2] : bj[2], iny2 = bj[3] > bi[3] ? bi[3] : bj[3];
+            float cxj = (bj[0] + bj[2]) / 2, cyj = (bj[1] + bj[3]) / 2;
+            float ddx = cxi - cxj, ddy = cyi - cyj;
+            float d = ddx * ddx + ddy * ddy;
+            float ox1 = bj[0] > bi[0] ? bi[0] : bj[0], oy1 = bj[1] > bi[1] ? bi[1] : bj[1];
+            float ox2 = bj[2] < bi[2] ? bi[2] : bj[2], oy2 = bj[3] < bi[3] ? bi[3] : bj[3];
+            float ex = ox2 - ox1, ey = oy2 - oy1;
+            float c = ex * ex + ey * ey;
+            float u = d / c;
+            float w = inx2 - inx1, h = iny2 - iny1;
+            if (w < 0.0f) w = 0.0f;
+            if (h < 0.0f) h = 0.0f;
+            float inter = w * h;
+            float area_j = (bj[2] - bj[0]) * (bj[3] - bj[1]);
+            float uni = (area_j - inter) + area_i;
+            float pen = beta1 == 1.0f ? u : powf(u, beta1);
+            float metric = inter / uni - pen;
+            if (metric <= overlap) idx[w_++] = j;
+        }
+        m = w_;
+    }
+    free(idx);
+    return count;
+}
+
 /* ------------------------------------------------------- composed pipeline */
 
 /*

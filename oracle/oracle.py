@@ -56,6 +56,8 @@ def lib():
         L.orc_nms_tv.argtypes = [c_f, c_f, ctypes.c_int64, ctypes.c_double, c_l]
         L.orc_nms_ssd.restype = ctypes.c_int64
         L.orc_nms_ssd.argtypes = [c_f, c_l, ctypes.c_int64, ctypes.c_float, ctypes.c_int64, c_l]
+        L.orc_diounms.restype = ctypes.c_int64
+        L.orc_diounms.argtypes = [c_f, c_l, ctypes.c_int64, ctypes.c_float, ctypes.c_int64, ctypes.c_float, c_l]
         L.orc_detect.restype = ctypes.c_int64
         L.orc_detect.argtypes = [c_f, c_f, c_f, c_f, ctypes.c_int64, ctypes.c_float, ctypes.c_float,
                                  ctypes.c_float, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
@@ -208,6 +210,18 @@ def nms_ssd(boxes, scores, overlap=0.5, top_k=200, order_asc=None):
     o = np.ascontiguousarray(order_asc, dtype=np.int64)
     keep = np.zeros((max(n, 1),), np.int64)
     c = lib().orc_nms_ssd(_pf(b), _pl(o), n, overlap, top_k, _pl(keep))
+    return keep[:n], int(c)
+
+
+def diounms(boxes, scores, overlap=0.5, top_k=200, beta1=1.0, order_asc=None):
+    """DIoU-NMS, R/utils/utils_bbox.py:182-258.  Returns (keep[n] zero-padded int64, count); ties like ``nms_ssd``."""
+    b, s = _f(boxes).reshape(-1, 4), _f(scores)
+    n = b.shape[0]
+    if order_asc is None:
+        order_asc = np.argsort(s, kind="stable")
+    o = np.ascontiguousarray(order_asc, dtype=np.int64)
+    keep = np.zeros((max(n, 1),), np.int64)
+    c = lib().orc_diounms(_pf(b), _pl(o), n, overlap, top_k, beta1, _pl(keep))
     return keep[:n], int(c)
 
 

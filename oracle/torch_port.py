@@ -81,15 +81,16 @@ def assign_one(thr, truths, priors, var, labels, landms, loc_t, conf_t, landm_t,
     return bt_idx, bt_ov, bp_idx
 
 
-def assign_batch(thr, targets, priors, var):
-    """The loop of MultiBoxLoss.forward, R/nets/retinaface_training.py:197-214."""
+def assign_batch(thr, targets, priors, var, encode=True):
+    """The loop of MultiBoxLoss.forward, R/nets/retinaface_training.py:197-214 (``encode=False``: match_iou,
+    R/nets/retinaface_training_DIOU.py:176-246)."""
     n, P = len(targets), priors.size(0)
     loc_t = torch.Tensor(n, P, 4)
     landm_t = torch.Tensor(n, P, 10)
     conf_t = torch.LongTensor(n, P)
     for i in range(n):
         t = targets[i]
-        assign_one(thr, t[:, :4], priors, var, t[:, -1], t[:, 4:14], loc_t, conf_t, landm_t, i)
+        assign_one(thr, t[:, :4], priors, var, t[:, -1], t[:, 4:14], loc_t, conf_t, landm_t, i, 0, 1 if encode else 0)
     return loc_t, conf_t, landm_t
 
 
@@ -99,20 +100,63 @@ def global_lse(x):
     return torch.log(torch.sum(torch.exp(x - m), 1, keepdim=True)) + m
 
 
-def multibox_loss(predictions, priors, targets, thr=0.35, var=(0.1, 0.2), negpos_ratio=7, return_aux=False):
+def overlaps_family(b1, b2, kind):
+    """bbox_overlaps_{iou,giou,diou,ciou}, R/utils/box_utils.py:5-158 (= R/nets/retinaface_training_DIOU.py:342-490):
+    row i of b1 against row i of b2; differentiable like the reference."""
+    import math
+    if b1.shape[0] * b2.shape[0] == 0:
+        return torch.zeros((b1.shape[0], b2.shape[0]))
+    if b1.shape[0] > b2.shape[0]:
+        b1, b2 = b2, b1
+    wh1, wh2 = b1[:, 2:] - b1[:, :2], b2[:, 2:] - b2[:, :2]
+    a1, a2 = wh1[:, 0] * wh1[:, 1], wh2[:, 0] * wh2[:, 1]
+    isz = torch.clamp(torch.min(b1[:, 2:], b2[:, 2:]) - torch.max(b1[:, :2], b2[:, :2]), min=0)
+    inter = isz[:, 0] * isz[:, 1]
+    union = a1 + a2 - inter
+    if kind == "iou":
+        return torch.clamp(inter / union, min=0, max=1.0)
+    osz = torch.clamp(torch.max(b1[:, 2:], b2[:, 2:]) - torch.min(b1[:, :2], b2[:, :2]), min=0)
+    if kind == "giou":
+        closure = osz[:, 0] * osz[:, 1]
+        return torch.clamp(inter / union - (closure - union) / closure, min=-1.0, max=1.0)
+    c1, c2 = (b1[:, 2:] + b1[:, :2]) / 2, (b2[:, 2:] + b2[:, :2]) / 2
+    centre = (c2[:, 0] - c1[:, 0]) ** 2 + (c2[:, 1] - c1[:, 1]) ** 2
+    diag = osz[:, 0] ** 2 + osz[:, 1] ** 2
+    if kind == "diou":
+        return torch.clamp(inter / union - centre / diag, min=-1.0, max=1.0)
+    u, iou = centre / diag, inter / union
+    v = (4 / (math.pi ** 2)) * torch.pow(torch.atan(wh2[:, 0] / wh2[:, 1]) - torch.atan(wh1[:, 0] / wh1[:, 1]), 2)
+    with torch.no_grad():
+        alpha = v / ((1 - iou) + v)
+    return torch.clamp(iou - (u + alpha * v), min=-1.0, max=1.0)
+
+
+def iou_loss(loc_p, loc_t, prior_data, var, kind, center=True, size_sum=True):
+    """IouLoss.forward, R/nets/retinaface_training_DIOU.py:491-525."""
+    boxes = decode_boxes(loc_p, prior_data, var) if center else loc_p
+    loss = torch.sum(1.0 - overlaps_family(boxes, loc_t, kind))
+    return loss if size_sum else loss / loc_p.shape[0]
+
+
+def multibox_loss(predictions, priors, targets, thr=0.35, var=(0.1, 0.2), negpos_ratio=7, return_aux=False, loc_loss=None):
     """MultiBoxLoss.forward with cuda=False; R/nets/retinaface_training.py:183-303.  ``predictions`` =
-    (loc_data [B,P,4], conf_data [B,P,2], landm_data [B,P,10]) CPU tensors (may require grad)."""
+    (loc_data [B,P,4], conf_data [B,P,2], landm_data [B,P,10]) CPU tensors (may require grad).  ``loc_loss`` "iou" / "giou" /
+    "diou" / "ciou": the variant of R/nets/retinaface_training_DIOU.py:527-665 (match_iou targets, IouLoss box term)."""
     import torch.nn.functional as F
     loc_data, conf_data, landm_data = predictions
     n = loc_data.size(0)
-    loc_t, conf_t, landm_t = assign_batch(thr, [t.data for t in targets], priors.data, list(var))
+    loc_t, conf_t, landm_t = assign_batch(thr, [t.data for t in targets], priors.data, list(var), encode=loc_loss is None)
     zero = torch.tensor(0)
     lm_pos = conf_t > zero                                           # :243
     lm_sel = lm_pos.unsqueeze(lm_pos.dim()).expand_as(landm_data)
     loss_landm = F.smooth_l1_loss(landm_data[lm_sel].view(-1, 10), landm_t[lm_sel].view(-1, 10), reduction='sum')
     pos = conf_t != zero                                             # :250
     box_sel = pos.unsqueeze(pos.dim()).expand_as(loc_data)
-    loss_l = F.smooth_l1_loss(loc_data[box_sel].view(-1, 4), loc_t[box_sel].view(-1, 4), reduction='sum')
+    if loc_loss is None:
+        loss_l = F.smooth_l1_loss(loc_data[box_sel].view(-1, 4), loc_t[box_sel].view(-1, 4), reduction='sum')
+    else:                                                            # DIOU.py:606-607
+        pri_sel = priors.data.unsqueeze(0).expand_as(loc_data)[box_sel].view(-1, 4)
+        loss_l = iou_loss(loc_data[box_sel].view(-1, 4), loc_t[box_sel].view(-1, 4), pri_sel, var, loc_loss)
     conf_t[pos] = 1                                                  # :259
     flat = conf_data.view(-1, 2)
     rank_val = global_lse(flat) - flat.gather(1, conf_t.view(-1, 1)) # :265

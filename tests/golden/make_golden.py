@@ -510,6 +510,81 @@ def gen_wider_eval(R):
     save("wider_eval.npz", **out)
 
 
+# ----------------------------------------------------------------------------- IoU family
+def family_boxes(n=600, seed=77):
+    """Aligned box pairs: jittered copies (high IoU), random pairs (mostly disjoint), nested, identical and
+    edge-sharing pairs -- every branch of the clamps / min / max."""
+    rng = np.random.default_rng(seed)
+    c = rng.random((n, 2)).astype(np.float32)
+    wh = (0.02 + 0.3 * rng.random((n, 2))).astype(np.float32)
+    a = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    b = a + (0.05 * rng.standard_normal((n, 4)) * np.concatenate([wh, wh], 1)).astype(np.float32)
+    b[: n // 4] = np.roll(a[: n // 4], 7, axis=0)                      # unrelated boxes
+    b[n // 4: n // 4 + 20] = a[n // 4: n // 4 + 20]                      # identical
+    k = n // 4 + 20
+    b[k: k + 20, :2] = a[k: k + 20, :2] + 0.25 * wh[k: k + 20]          # nested
+    b[k: k + 20, 2:] = a[k: k + 20, 2:] - 0.25 * wh[k: k + 20]
+    b[k + 20: k + 40] = a[k + 20: k + 40] + np.float32([1, 0, 1, 0]) * (a[k + 20: k + 40, 2:3] - a[k + 20: k + 40, 0:1])  # touching
+    b[:, 2:] = np.maximum(b[:, 2:], b[:, :2] + np.float32(1e-3))
+    return a, b.astype(np.float32)
+
+
+DIOU_LOSS_CASES = [("s160", (160, 160), 3, None), ("s320", (320, 320), 2, 40)]
+
+
+def gen_iou_family(R):
+    """bbox_overlaps_{iou,giou,diou,ciou} (R/utils/box_utils.py:5-158), IouLoss + autograd and the DIoU MultiBoxLoss
+    (R/nets/retinaface_training_DIOU.py:491-665, cuda=False), diounms (R/utils/utils_bbox.py:182-258)."""
+    r_anchors, r_config, r_box_utils, r_utils_bbox, _, r_diou = R
+    out = {}
+    a, b = family_boxes()
+    out["a"], out["b"] = a, b
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+    for kind in ("iou", "giou", "diou", "ciou"):
+        out["ov_" + kind] = getattr(r_box_utils, "bbox_overlaps_" + kind)(ta, tb).numpy()
+        assert np.array_equal(getattr(r_diou, "bbox_overlaps_" + kind)(ta, tb).numpy(), out["ov_" + kind], equal_nan=True), kind
+    out["ov_diou_bcast"] = r_box_utils.bbox_overlaps_diou(ta[:1], tb).numpy()          # one row against many
+    # IouLoss on decoded predictions, all loss types, with autograd
+    pri = r_anchors.Anchors(r_config.cfg_mnet, image_size=(160, 160)).get_anchors()[:600].contiguous()
+    g = torch.Generator().manual_seed(5)
+    enc = r_diou.encode(tb.clamp(0.01, 0.99), pri, VAR) if hasattr(r_diou, "encode") else None
+    loc = (enc + 0.3 * torch.randn(enc.shape, generator=g)).clamp(-4, 4)
+    out["loss_loc"], out["loss_pri"] = loc.numpy(), pri.numpy()
+    for lt in ("Iou", "Giou", "Diou", "Ciou"):
+        for size_sum in (True, False):
+            lp = loc.clone().requires_grad_(True)
+            crit = r_diou.IouLoss(pred_mode='Center', size_sum=size_sum, variances=VAR, losstype=lt)
+            val = crit(lp, tb, pri)
+            val.backward()
+            tag = "%s_%d" % (lt, int(size_sum))
+            out["loss_" + tag], out["grad_" + tag] = np.array(val.item(), np.float32), lp.grad.numpy()
+    lp = ta.clone().requires_grad_(True)
+    val = r_diou.IouLoss(pred_mode='Corner', size_sum=True, variances=VAR, losstype='Giou')(lp, tb, pri)
+    val.backward()
+    out["loss_corner_giou"], out["grad_corner_giou"] = np.array(val.item(), np.float32), lp.grad.numpy()
+    # the DIoU MultiBoxLoss
+    for tag, size, batch, count in DIOU_LOSS_CASES:
+        pri2, targets, preds = loss_inputs(r_anchors, r_config.cfg_mnet, size, batch, count)
+        crit = r_diou.MultiBoxLoss(2, THR, 7, VAR, False)
+        l, c, m = crit(preds, pri2, targets)
+        (1.0 * l + 2.0 * c + 0.5 * m).backward()
+        out["mbl_%s_losses" % tag] = np.array([l.item(), c.item(), m.item()], dtype=np.float32)
+        g_loc, g_conf, g_landm = (p.grad.numpy() for p in preds)
+        out["mbl_%s_sel" % tag] = np.packbits((np.abs(g_conf).sum(2) != 0))
+        nzl = np.flatnonzero(np.abs(g_loc).sum(2).reshape(-1))
+        out["mbl_%s_g_loc_nz_idx" % tag] = nzl.astype(np.int32)
+        out["mbl_%s_g_loc_nz" % tag] = g_loc.reshape(-1, 4)[nzl]
+    # diounms on the NMS fixtures' boxes
+    nms = np.load(os.path.join(HERE, "nms.npz"))
+    for name in ("rand500", "dense2000"):
+        bx, sc = torch.from_numpy(nms[name + "_boxes"]), torch.from_numpy(nms[name + "_scores"])
+        assert len(np.unique(nms[name + "_scores"])) == len(nms[name + "_scores"])   # the unstable sort has one answer
+        for (ov, tk, beta) in ((0.5, 200, 1.0), (0.3, 5000, 1.0), (0.45, 5000, 0.6)):
+            keep, count = r_utils_bbox.diounms(bx, sc, ov, tk, beta)
+            out["dnms_%s_%d_%d_%d_keep" % (name, int(ov * 100), tk, int(beta * 10))] = keep.numpy()[:count]
+    save("iou_family.npz", **out)
+
+
 def main():
     R = import_reference()
     gen_priors(R)
@@ -520,6 +595,7 @@ def main():
     gen_loss(R)
     gen_post(R)
     gen_wider_eval(R)
+    gen_iou_family(R)
     if "--check" in sys.argv:
         sys.exit(1 if check(R) else 0)
 

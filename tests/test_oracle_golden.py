@@ -295,3 +295,35 @@ def test_wider_eval_oracle_matches_reference():
         pr = ow.pr_counters(normed, [im[0] for im in imgs], [im[1][s] for im in imgs], 0.4, 1000)
         np.testing.assert_array_equal(pr, g["pr_curve_" + name])
         assert ow.average_precision(pr, int(g["count_face_" + name])) == float(g["ap_" + name])
+
+
+def test_iou_family_torch_port_and_c_oracle():
+    """oracle/torch_port.overlaps_family / iou_loss / multibox_loss(loc_loss="diou") and
+    oracle.diounms reproduce the reference (box_utils.bbox_overlaps_*, DIOU.IouLoss, DIOU.MultiBoxLoss, utils_bbox.diounms)."""
+    g = load_golden("iou_family.npz")
+    a, b = torch.from_numpy(g["a"]), torch.from_numpy(g["b"])
+    for kind in ("iou", "giou", "diou", "ciou"):
+        np.testing.assert_array_equal(tp.overlaps_family(a, b, kind).numpy(), g["ov_" + kind])
+    np.testing.assert_array_equal(tp.overlaps_family(a[:1], b, "diou").numpy(), g["ov_diou_bcast"])
+    loc, pri = torch.from_numpy(g["loss_loc"]), torch.from_numpy(g["loss_pri"])
+    for lt in ("Iou", "Giou", "Diou", "Ciou"):
+        for size_sum in (True, False):
+            lp = loc.clone().requires_grad_(True)
+            val = tp.iou_loss(lp, b, pri, [0.1, 0.2], lt.lower(), True, size_sum)
+            val.backward()
+            tag = "%s_%d" % (lt, int(size_sum))
+            assert np.float32(val.item()) == g["loss_" + tag]
+            np.testing.assert_array_equal(lp.grad.numpy(), g["grad_" + tag])
+    for tag, size, batch, count in (("s160", (160, 160), 3, None), ("s320", (320, 320), 2, 40)):
+        pri2, targets, preds = _loss_inputs(size, batch, count)
+        l, c, m = tp.multibox_loss(preds, pri2, targets, 0.35, [0.1, 0.2], 7, loc_loss="diou")
+        (1.0 * l + 2.0 * c + 0.5 * m).backward()
+        np.testing.assert_array_equal(np.array([l.item(), c.item(), m.item()], dtype=np.float32), g["mbl_%s_losses" % tag])
+        g_loc, g_conf = preds[0].grad.numpy(), preds[1].grad.numpy()
+        np.testing.assert_array_equal(np.packbits(np.abs(g_conf).sum(2) != 0), g["mbl_%s_sel" % tag])
+        np.testing.assert_array_equal(g_loc.reshape(-1, 4)[g["mbl_%s_g_loc_nz_idx" % tag]], g["mbl_%s_g_loc_nz" % tag])
+    nms = load_golden("nms.npz")
+    for name in ("rand500", "dense2000"):
+        for (ov, tk, beta) in ((0.5, 200, 1.0), (0.3, 5000, 1.0), (0.45, 5000, 0.6)):
+            keep, count = orc.diounms(nms[name + "_boxes"], nms[name + "_scores"], ov, tk, beta)
+            np.testing.assert_array_equal(keep[:count], g["dnms_%s_%d_%d_%d_keep" % (name, int(ov * 100), tk, int(beta * 10))])
