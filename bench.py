@@ -10,6 +10,7 @@ Per-GPU work is fixed (weak scaling): N ranks process N*32 images per step with 
 One JSON line is printed by rank 0.
 """
 import argparse
+import numpy as np
 import json
 import os
 import statistics
@@ -525,6 +526,55 @@ def main():
                                                   "l2": "4 rotating in/out sets of 64 images"}
             del big, outs, outb
 
+    # ---- cfg5 validation flow: detect the rank's shard, scale to pixels, all-gather the padded detections (the path's only
+    # collective, NCCL over NVLink), WIDER AP of the gathered set on rank 0 (SURVEY 8e + 8f ranks 2-3)
+    cfg5_info = None
+    if not args.no_extras:
+        from jabd_b200 import utils_map
+        size, B5 = (640, 640), 32
+        pr5 = anchors.cached_priors(config.cfg_mnet, size, dev)
+        locs, confs, lms = [], [], []
+        for i in range(B5):
+            gi = rank * B5 + i
+            l, c, m = synth.make_preds_clustered(5, gi, pr5, synth.make_gt(5, gi, size, count=40), VAR, device=dev)
+            locs.append(l); confs.append(c); lms.append(m)
+        loc5, conf5, lm5 = (torch.stack(x).contiguous().to(dev) for x in (locs, confs, lms))   # resident in HBM
+        post5 = torch.from_numpy(batched.letterbox_params(size, [size] * B5)).to(dev)
+
+        def cfg5_step():
+            d, c, _ = batched.detect(loc5, conf5, lm5, pr5, VAR)
+            batched.correct_boxes(d, c, post5, letterbox=False, to_pixels=True)
+            return sharding.allgather_detections(d, c)
+        for _ in range(3):
+            gd, gc = cfg5_step()
+        n5 = 20
+        ms5, _ = timed_loop(lambda k: cfg5_step(), n5)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d_loc, c_loc, _ = batched.detect(loc5, conf5, lm5, pr5, VAR)
+        barrier()
+        e0.record()
+        for _ in range(n5):
+            sharding.allgather_detections(d_loc, c_loc)
+        e1.record()
+        barrier()
+        us_ag = max_over_ranks(e0.elapsed_time(e1)) / n5 * 1e3
+        cfg5_info = {"images_per_s": world * B5 * n5 / (ms5 / 1e3), "ms_per_step": ms5 / n5, "allgather_us": us_ag,
+                     "allgather_bytes_per_rank": int(d_loc.numel() * 4 + c_loc.numel() * 4),
+                     "what": "per rank: fused detect of 32 x 640^2 images (score>0.02, top-5000, IoU 0.4, keep 750) + pixel scaling, then "
+                             "one all_gather_into_tensor of dets [32,750,15] + counts over %s" % ("NCCL" if world > 1 else "a single rank (no-op)")}
+        if rank == 0:
+            preds5 = utils_map.dets_to_pred_rows(gd, gc)
+            gts5, keeps5 = [], []
+            for gi in range(world * B5):
+                t5 = synth.make_gt(5, gi, size, count=40)[:, :4].numpy().astype("float64") * size[0]
+                gts5.append(np.stack([t5[:, 0], t5[:, 1], t5[:, 2] - t5[:, 0], t5[:, 3] - t5[:, 1]], 1))
+                keeps5.append(np.ones(t5.shape[0], np.uint8))
+            t0 = time.perf_counter()
+            ap5 = utils_map.evaluate_arrays(preds5, gts5, [keeps5], 0.4, 1000)
+            cfg5_info["ap_eval_ms"] = (time.perf_counter() - t0) * 1e3
+            cfg5_info["ap_all_faces"] = float(ap5[0])
+            cfg5_info["ap_images"] = world * B5
+
     clocks = None
     if sampler is not None:
         sampler.stop()
@@ -567,7 +617,7 @@ def main():
                    "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2), one CUDA graph each"
                          % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "phases": phases,
-        "detect": detect_info, "loss": loss_info,
+        "detect": detect_info, "loss": loss_info, "cfg5_eval": cfg5_info,
     }
     emit(line)
     return 0
