@@ -65,6 +65,10 @@ __device__ __forceinline__ float rank_value(float2 c, float M)
     return fsub(fadd(log_f32(s), M), c.x);
 }
 
+struct LossFwdArgs;
+__device__ __forceinline__ uint32_t rank_bits(const LossFwdArgs &a, const uint32_t *s_rank, int cache_cap, long long row0, long long p,
+                                              float M);
+
 __global__ void __launch_bounds__(256) mbl_max_kernel(const float *__restrict__ x, long long n, unsigned *out)
 {
     unsigned m = 0;
@@ -131,8 +135,20 @@ struct LossFwdArgs {
     float var0, var1;
 };
 
-__global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArgs a)
+__device__ __forceinline__ uint32_t rank_bits(const LossFwdArgs &a, const uint32_t *s_rank, int cache_cap, long long row0, long long p,
+                                              float M)
 {
+    if (p < cache_cap) return s_rank[p];
+    const bool pos = a.conf_t[row0 + p] != 0;
+    return ord_of(pos ? 0.0f : rank_value(__ldg(a.conf_data + row0 + p), M));
+}
+
+// The order-preserving bits of every prior's rank value are computed once (pass 1) and kept in dynamic shared memory
+// (`cache_cap` entries; priors beyond that are recomputed in the later passes), so the two exp + one log per prior are
+// not paid four times.
+__global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArgs a, int cache_cap)
+{
+    extern __shared__ __align__(16) uint32_t s_rank[];
     __shared__ LossSmem sm;
     const int tid = threadIdx.x;
     const unsigned lane = lane_id();
@@ -146,13 +162,26 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
     for (int i = tid; i < kLossBins; i += kLossThreads) sm.hist[i] = 0;
     __syncthreads();
     int npos = 0, npos1 = 0;
-    for (long long p = tid; p < P; p += kLossThreads) {
-        const long long ct = a.conf_t[row0 + p];
-        const bool pos = ct != 0;
-        npos += pos ? 1 : 0;
-        npos1 += ct > 0 ? 1 : 0;
-        const float v = pos ? 0.0f : rank_value(__ldg(a.conf_data + row0 + p), M);
-        atomicAdd(&sm.hist[ord_of(v) >> 21], 1u);
+    for (long long base = tid; base < P; base += 4ll * kLossThreads) { // four loads in flight before the first atomic
+        long long ct[4];
+        float2 cd[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long p = base + (long long)k * kLossThreads;
+            ct[k] = p < P ? a.conf_t[row0 + p] : 1;
+            cd[k] = p < P ? __ldg(a.conf_data + row0 + p) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long p = base + (long long)k * kLossThreads;
+            if (p >= P) continue;
+            const bool pos = ct[k] != 0;
+            npos += pos ? 1 : 0;
+            npos1 += ct[k] > 0 ? 1 : 0;
+            const uint32_t u = ord_of(pos ? 0.0f : rank_value(cd[k], M));
+            if (p < cache_cap) s_rank[p] = u;
+            atomicAdd(&sm.hist[u >> 21], 1u);
+        }
     }
     npos = __reduce_add_sync(kFull, npos);
     npos1 = __reduce_add_sync(kFull, npos1);
@@ -181,8 +210,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
         for (int i = tid; i < kLossBins; i += kLossThreads) sm.hist[i] = 0;
         __syncthreads();
         for (long long p = tid; p < P; p += kLossThreads) {
-            const bool pos = a.conf_t[row0 + p] != 0;
-            const uint32_t u = ord_of(pos ? 0.0f : rank_value(__ldg(a.conf_data + row0 + p), M));
+            const uint32_t u = rank_bits(a, s_rank, cache_cap, row0, p, M);
             if ((u >> 21) == b1) atomicAdd(&sm.hist[(u >> 10) & 0x7ffu], 1u);
         }
         __syncthreads();
@@ -194,8 +222,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
         for (int i = tid; i < 1024; i += kLossThreads) sm.hist[i] = 0;
         __syncthreads();
         for (long long p = tid; p < P; p += kLossThreads) {
-            const bool pos = a.conf_t[row0 + p] != 0;
-            const uint32_t u = ord_of(pos ? 0.0f : rank_value(__ldg(a.conf_data + row0 + p), M));
+            const uint32_t u = rank_bits(a, s_rank, cache_cap, row0, p, M);
             if ((u >> 10) == pre) atomicAdd(&sm.hist[u & 0x3ffu], 1u);
         }
         __syncthreads();
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
             pos1 = ct > 0;
             c = __ldg(a.conf_data + row0 + p);
             if (want > 0) {
-                const uint32_t u = ord_of(pos ? 0.0f : rank_value(c, M));
+                const uint32_t u = p < cache_cap ? s_rank[p] : ord_of(pos ? 0.0f : rank_value(c, M));
                 neg = u > T;
                 tie = u == T;
             }
@@ -444,7 +471,18 @@ int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data,
         a.priors = reinterpret_cast<const float4 *>(priors);
         a.var0 = var0;
         a.var1 = var1;
-        mbl_forward_kernel<<<(unsigned)B, kLossThreads, 0, st>>>(a);
+        // rank-value cache: as many priors as fit next to the kernel's static shared memory (opt-in above 48 KB)
+        constexpr long long kCacheMax = 48 * 1024;   // entries (192 KB)
+        const int cache_cap = (int)(P < kCacheMax ? P : kCacheMax);
+        const size_t dyn = sizeof(uint32_t) * (size_t)cache_cap;
+        static bool attr_done[64] = {};
+        int devi = 0;
+        JABD_CUDA(cudaGetDevice(&devi));
+        if (!(devi >= 0 && devi < 64 && attr_done[devi])) {
+            JABD_CUDA(cudaFuncSetAttribute(mbl_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * kCacheMax)));
+            if (devi >= 0 && devi < 64) attr_done[devi] = true;
+        }
+        mbl_forward_kernel<<<(unsigned)B, kLossThreads, dyn, st>>>(a, cache_cap);
         JABD_LAUNCH_CHECK("mbl_forward_kernel");
     }
     mbl_finalize_kernel<<<1, 32, 0, st>>>(ws, (B > 0 && P > 0) ? B : 0, losses, norms);

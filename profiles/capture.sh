@@ -14,8 +14,10 @@ python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_refere
 # 2. launch list of the bench command: every kernel with its device time (cold-cache, serialised: compare shares)
 $BENCH > $out/${tag}_plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv $BENCH > $out/${tag}_ncu_launch.log 2>&1
-# 3. full capture of the hot kernels on BASELINE shapes (prof_run.py: cfg2 assign, cfg3 detect, decode)
+# 3. full capture of the hot kernels on BASELINE shapes (prof_run.py: cfg2 assign + loss, cfg3 detect, decode, AP eval):
+#    one profiled pass after warm-up (cudaProfilerStart/Stop inside prof_run.py)
 $PROF > $out/${tag}_plain_prof.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"assign_|match_encode|detect_kernel|decode_kernel" -s 9 -c 8 \
+ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:"assign_|match_encode|detect_kernel|decode_kernel|mbl_|wider_eval_kernel" -c 24 \
     -f -o $out/${tag}_full $PROF > $out/${tag}_ncu_full.log 2>&1
 tail -2 $out/${tag}_ncu_full.log

@@ -71,7 +71,8 @@ def full():
     seen = {}
     with open(os.path.join(dst, tag + "_ncu_summary.txt"), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on, command: python profiles/prof_run.py all\n"
-                "# (cfg2 target assignment: 32 x 640^2 images, 16,800 priors; cfg3 detection: 16 x 1024^2, 43,008 priors)\n"
+                "# (one profiled pass after warm-up.  cfg2 target assignment + MultiBox loss fwd/bwd, smooth-L1 and DIoU box terms: 32 x 640^2\n"
+                "#  images, 16,800 priors; cfg3 detection: 16 x 1024^2, 43,008 priors; decode: 64 x 1024^2; WIDER AP counters: 256 images)\n"
                 "# under ncu every launch is replayed ~40x with caches flushed: durations are not bench numbers\n")
         for r in rows[2:]:
             k = short(r[ki])
