@@ -18,16 +18,24 @@
 //   mbl_forward_kernel   per image: counts, radix select, selection mask [B,P] (bit0 pos, bit1 pos1, bit2 neg), partial sums
 //   mbl_finalize_kernel  batch sums -> losses[3], norms[2]
 //   mbl_backward_kernel  per prior: gradients of the three losses w.r.t. loc_data / conf_data / landm_data
+#include <cooperative_groups.h>
+
 #include "iou_family.cuh"
 
 namespace jabd {
 
+namespace cg = cooperative_groups;
+
 constexpr int kLossThreads = 1024;
 constexpr int kLossBins = 2048;
+#ifndef JABD_LOSS_CLUSTER
+#define JABD_LOSS_CLUSTER 4
+#endif
+constexpr int kLossCluster = JABD_LOSS_CLUSTER; // CTAs (SMs) per image: a thread-block cluster whose histograms meet in distributed shared memory
 
 struct LossWs {
     unsigned *xmax;   // [1] ordered bits of max(conf_data)
-    double *partial;  // [B,4] sum_l, sum_c, sum_landm, (unused)
+    double *partial;  // [B*kLossCluster,4] sum_l, sum_c, sum_landm, (unused): one row per CTA
     int *counts;      // [B,2] num_pos, num_pos1
 };
 
@@ -41,7 +49,7 @@ static size_t loss_ws_layout(int B, LossWs *w, char *base)
     };
     const size_t nb = (size_t)(B > 0 ? B : 1);
     size_t o_x = take(sizeof(unsigned) * 4);
-    size_t o_p = take(sizeof(double) * 4 * nb);
+    size_t o_p = take(sizeof(double) * 4 * nb * kLossCluster);
     size_t o_c = take(sizeof(int) * 2 * nb);
     if (w) {
         w->xmax = reinterpret_cast<unsigned *>(base + o_x);
@@ -67,7 +75,7 @@ __device__ __forceinline__ float rank_value(float2 c, float M)
 
 struct LossFwdArgs;
 __device__ __forceinline__ uint32_t rank_bits(const LossFwdArgs &a, const uint32_t *s_rank, int cache_cap, long long row0, long long p,
-                                              float M);
+                                              long long p_lo, float M);
 
 __global__ void __launch_bounds__(256) mbl_max_kernel(const float *__restrict__ x, long long n, unsigned *out)
 {
@@ -81,7 +89,10 @@ __global__ void __launch_bounds__(256) mbl_max_kernel(const float *__restrict__ 
 }
 
 struct LossSmem {
-    unsigned hist[kLossBins];
+    unsigned local[kLossBins];   // this CTA's histogram (read by the other CTAs of the cluster)
+    unsigned hist[kLossBins];    // the image's histogram: sum over the cluster
+    unsigned before[kLossBins];  // per bin: count in the CTAs of lower rank (index order of tied values)
+    int cnt_local[2];            // this CTA's num_pos, num_pos1
     unsigned wsum[32];
     unsigned wsum2[32];
     double dsum[3][32];
@@ -136,51 +147,83 @@ struct LossFwdArgs {
 };
 
 __device__ __forceinline__ uint32_t rank_bits(const LossFwdArgs &a, const uint32_t *s_rank, int cache_cap, long long row0, long long p,
-                                              float M)
+                                              long long p_lo, float M)
 {
-    if (p < cache_cap) return s_rank[p];
+    if (p - p_lo < cache_cap) return s_rank[p - p_lo];
     const bool pos = a.conf_t[row0 + p] != 0;
     return ord_of(pos ? 0.0f : rank_value(__ldg(a.conf_data + row0 + p), M));
 }
 
-// The order-preserving bits of every prior's rank value are computed once (pass 1) and kept in dynamic shared memory
-// (`cache_cap` entries; priors beyond that are recomputed in the later passes), so the two exp + one log per prior are
-// not paid four times.
+// One cluster of kLossCluster CTAs per image, CTA r owning the contiguous prior range r: the order-preserving bits of every
+// prior's rank value are computed once (pass 1) and kept in dynamic shared memory (`cache_cap` entries per CTA; priors
+// beyond that are recomputed in the later passes), each histogram is built locally and summed over the cluster through
+// distributed shared memory, so that every CTA finds the same cut without a global round trip.
+__device__ __forceinline__ void cluster_merge_hist(LossSmem &sm, int nbins, cg::cluster_group &cluster, bool with_counts)
+{
+    cluster.sync(); // every CTA's local histogram is complete
+    const unsigned rank = cluster.block_rank();
+    for (int i = threadIdx.x; i < nbins; i += kLossThreads) {
+        unsigned sum = 0, bef = 0;
+        for (unsigned r = 0; r < (unsigned)kLossCluster; ++r) {
+            const unsigned v = cluster.map_shared_rank(sm.local, r)[i];
+            sum += v;
+            if (r < rank) bef += v;
+        }
+        sm.hist[i] = sum;
+        sm.before[i] = bef;
+    }
+    if (with_counts && threadIdx.x == 0) {
+        int s0 = 0, s1 = 0;
+        for (unsigned r = 0; r < (unsigned)kLossCluster; ++r) {
+            const int *c = cluster.map_shared_rank(sm.cnt_local, r);
+            s0 += c[0];
+            s1 += c[1];
+        }
+        sm.total[0] = s0;
+        sm.total[1] = s1;
+    }
+    cluster.sync(); // nobody overwrites its local histogram while a neighbour still reads it
+}
+
 __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArgs a, int cache_cap)
 {
     extern __shared__ __align__(16) uint32_t s_rank[];
     __shared__ LossSmem sm;
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x;
     const unsigned lane = lane_id();
     const int warp = tid >> 5;
-    const int b = blockIdx.x;
+    const int crank = (int)cluster.block_rank();
+    const int b = blockIdx.x / kLossCluster;
     const long long P = a.P;
     const long long row0 = (long long)b * P;
+    const long long per = (P + kLossCluster - 1) / kLossCluster;
+    const long long p_lo = crank * per < P ? crank * per : P, p_hi = (p_lo + per) < P ? (p_lo + per) : P;
     const float M = ord_inv(a.ws.xmax[0]);
 
     // ---- pass 1: counts + top 11 bits of the rank value
-    for (int i = tid; i < kLossBins; i += kLossThreads) sm.hist[i] = 0;
+    for (int i = tid; i < kLossBins; i += kLossThreads) sm.local[i] = 0;
     __syncthreads();
     int npos = 0, npos1 = 0;
-    for (long long base = tid; base < P; base += 4ll * kLossThreads) { // four loads in flight before the first atomic
+    for (long long base = p_lo + tid; base < p_hi; base += 4ll * kLossThreads) { // four loads in flight before the first atomic
         long long ct[4];
         float2 cd[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const long long p = base + (long long)k * kLossThreads;
-            ct[k] = p < P ? a.conf_t[row0 + p] : 1;
-            cd[k] = p < P ? __ldg(a.conf_data + row0 + p) : make_float2(0.f, 0.f);
+            ct[k] = p < p_hi ? a.conf_t[row0 + p] : 1;
+            cd[k] = p < p_hi ? __ldg(a.conf_data + row0 + p) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const long long p = base + (long long)k * kLossThreads;
-            if (p >= P) continue;
+            if (p >= p_hi) continue;
             const bool pos = ct[k] != 0;
             npos += pos ? 1 : 0;
             npos1 += ct[k] > 0 ? 1 : 0;
             const uint32_t u = ord_of(pos ? 0.0f : rank_value(cd[k], M));
-            if (p < cache_cap) s_rank[p] = u;
-            atomicAdd(&sm.hist[u >> 21], 1u);
+            if (p - p_lo < cache_cap) s_rank[p - p_lo] = u;
+            atomicAdd(&sm.local[u >> 21], 1u);
         }
     }
     npos = __reduce_add_sync(kFull, npos);
@@ -190,45 +233,46 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
     if (tid == 0) {
         int s0 = 0, s1 = 0;
         for (int w = 0; w < kLossThreads / 32; ++w) { s0 += (int)sm.wsum[w]; s1 += (int)sm.wsum2[w]; }
-        sm.total[0] = s0;
-        sm.total[1] = s1;
+        sm.cnt_local[0] = s0;
+        sm.cnt_local[1] = s1;
     }
-    __syncthreads();
+    cluster_merge_hist(sm, kLossBins, cluster, true);
     const int num_pos = sm.total[0], num_pos1 = sm.total[1];
     long long want_ll = (long long)a.negpos_ratio * num_pos; // torch.clamp(negpos_ratio * num_pos, max = P - 1), :280
     if (want_ll > P - 1) want_ll = P - 1;
     const unsigned want = want_ll > 0 ? (unsigned)want_ll : 0u;
 
-    // ---- passes 2, 3: exact cut value T, number of elements above it, quota of ties
+    // ---- passes 2, 3: exact cut value T, number of elements above it, quota of ties (same decisions in every CTA)
     uint32_t T = 0xffffffffu;
-    unsigned quota = 0, eq_total = 0;
+    unsigned quota = 0, eq_total = 0, eq_before = 0;
     if (want > 0) {
         loss_find_bin(sm, kLossBins, want);
         const uint32_t b1 = sm.found_bin;
         const unsigned above1 = sm.found_above;
         __syncthreads();
-        for (int i = tid; i < kLossBins; i += kLossThreads) sm.hist[i] = 0;
+        for (int i = tid; i < kLossBins; i += kLossThreads) sm.local[i] = 0;
         __syncthreads();
-        for (long long p = tid; p < P; p += kLossThreads) {
-            const uint32_t u = rank_bits(a, s_rank, cache_cap, row0, p, M);
-            if ((u >> 21) == b1) atomicAdd(&sm.hist[(u >> 10) & 0x7ffu], 1u);
+        for (long long p = p_lo + tid; p < p_hi; p += kLossThreads) {
+            const uint32_t u = rank_bits(a, s_rank, cache_cap, row0, p, p_lo, M);
+            if ((u >> 21) == b1) atomicAdd(&sm.local[(u >> 10) & 0x7ffu], 1u);
         }
-        __syncthreads();
+        cluster_merge_hist(sm, kLossBins, cluster, false);
         loss_find_bin(sm, kLossBins, want - above1);
         const uint32_t b2 = sm.found_bin;
         const unsigned above2 = sm.found_above;
         __syncthreads();
         const uint32_t pre = (b1 << 11) | b2;
-        for (int i = tid; i < 1024; i += kLossThreads) sm.hist[i] = 0;
+        for (int i = tid; i < 1024; i += kLossThreads) sm.local[i] = 0;
         __syncthreads();
-        for (long long p = tid; p < P; p += kLossThreads) {
-            const uint32_t u = rank_bits(a, s_rank, cache_cap, row0, p, M);
-            if ((u >> 10) == pre) atomicAdd(&sm.hist[u & 0x3ffu], 1u);
+        for (long long p = p_lo + tid; p < p_hi; p += kLossThreads) {
+            const uint32_t u = rank_bits(a, s_rank, cache_cap, row0, p, p_lo, M);
+            if ((u >> 10) == pre) atomicAdd(&sm.local[u & 0x3ffu], 1u);
         }
-        __syncthreads();
+        cluster_merge_hist(sm, 1024, cluster, false);
         loss_find_bin(sm, 1024, want - above1 - above2);
         T = (pre << 10) | sm.found_bin;
         eq_total = sm.found_cnt;
+        eq_before = sm.before[sm.found_bin];
         quota = want - (above1 + above2 + sm.found_above);
         __syncthreads();
     }
@@ -236,18 +280,18 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
 
     // ---- final pass: selection mask and the three sums
     float sl = 0.0f, sc = 0.0f, sn = 0.0f;
-    unsigned eq_seen = 0;
-    for (long long base = 0; base < P; base += kLossThreads) {
+    unsigned eq_seen = eq_before; // ties at the cut value in the prior ranges of the lower-ranked CTAs come first
+    for (long long base = p_lo; base < p_hi; base += kLossThreads) {
         const long long p = base + tid;
         bool pos = false, pos1 = false, neg = false, tie = false;
         float2 c = make_float2(0.f, 0.f);
-        if (p < P) {
+        if (p < p_hi) {
             const long long ct = a.conf_t[row0 + p];
             pos = ct != 0;
             pos1 = ct > 0;
             c = __ldg(a.conf_data + row0 + p);
             if (want > 0) {
-                const uint32_t u = p < cache_cap ? s_rank[p] : ord_of(pos ? 0.0f : rank_value(c, M));
+                const uint32_t u = (p - p_lo) < cache_cap ? s_rank[p - p_lo] : ord_of(pos ? 0.0f : rank_value(c, M));
                 neg = u > T;
                 tie = u == T;
             }
@@ -269,7 +313,7 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
         } else {
             neg = neg || tie;
         }
-        if (p < P) {
+        if (p < p_hi) {
             a.mask[row0 + p] = (unsigned char)((pos ? 1 : 0) | (pos1 ? 2 : 0) | (neg ? 4 : 0));
             if (pos || neg) { // cross entropy with target = pos ? 1 : 0 (conf_t[pos] = 1, :259), stable log-softmax
                 const float mx = fmaxf(c.x, c.y);
@@ -306,11 +350,14 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
     if (tid == 0) {
         double tl = 0.0, tc = 0.0, tn = 0.0;
         for (int w = 0; w < kLossThreads / 32; ++w) { tl += sm.dsum[0][w]; tc += sm.dsum[1][w]; tn += sm.dsum[2][w]; }
-        a.ws.partial[4 * b + 0] = tl;
-        a.ws.partial[4 * b + 1] = tc;
-        a.ws.partial[4 * b + 2] = tn;
-        a.ws.counts[2 * b + 0] = num_pos;
-        a.ws.counts[2 * b + 1] = num_pos1;
+        double *out = a.ws.partial + 4 * ((size_t)b * kLossCluster + crank);
+        out[0] = tl;
+        out[1] = tc;
+        out[2] = tn;
+        if (crank == 0) {
+            a.ws.counts[2 * b + 0] = num_pos;
+            a.ws.counts[2 * b + 1] = num_pos1;
+        }
     }
 }
 
@@ -320,9 +367,12 @@ __global__ void __launch_bounds__(32) mbl_finalize_kernel(LossWs ws, int B, floa
     double tl = 0.0, tc = 0.0, tn = 0.0;
     long long n = 0, n1 = 0;
     for (int b = 0; b < B; ++b) {
-        tl += ws.partial[4 * b + 0];
-        tc += ws.partial[4 * b + 1];
-        tn += ws.partial[4 * b + 2];
+        for (int r = 0; r < kLossCluster; ++r) { // fixed order: images, then the cluster's CTAs
+            const double *q = ws.partial + 4 * ((size_t)b * kLossCluster + r);
+            tl += q[0];
+            tc += q[1];
+            tn += q[2];
+        }
         n += ws.counts[2 * b + 0];
         n1 += ws.counts[2 * b + 1];
     }
@@ -438,7 +488,7 @@ int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data,
     JABD_REQUIRE(loc_loss == 0 || (priors && aligned_to(priors, 16)), JABD_EINVAL,
                  "multibox_loss: the IoU-family box loss needs 16-byte aligned priors");
     JABD_REQUIRE(B >= 0 && P >= 0 && negpos_ratio >= 0, JABD_EINVAL, "multibox_loss: negative size");
-    JABD_REQUIRE(B <= 65535 && (int64_t)B * P < (1ll << 40), JABD_EINVAL, "multibox_loss: batch too large");
+    JABD_REQUIRE(B <= (1 << 20) && (int64_t)B * P < (1ll << 40), JABD_EINVAL, "multibox_loss: batch too large");
     JABD_REQUIRE(losses && norms, JABD_EINVAL, "multibox_loss: null output pointer");
     JABD_REQUIRE(workspace && aligned_to(workspace, 256), JABD_EWORKSPACE, "multibox_loss: workspace null or not 256-byte aligned");
     JABD_REQUIRE(workspace_bytes >= loss_ws_layout(B, nullptr, nullptr), JABD_EWORKSPACE, "multibox_loss: workspace too small");
@@ -471,9 +521,10 @@ int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data,
         a.priors = reinterpret_cast<const float4 *>(priors);
         a.var0 = var0;
         a.var1 = var1;
-        // rank-value cache: as many priors as fit next to the kernel's static shared memory (opt-in above 48 KB)
+        // rank-value cache: as many priors of a CTA's range as fit next to the kernel's static shared memory (opt-in > 48 KB)
         constexpr long long kCacheMax = 48 * 1024;   // entries (192 KB)
-        const int cache_cap = (int)(P < kCacheMax ? P : kCacheMax);
+        const long long per = (P + kLossCluster - 1) / kLossCluster;
+        const int cache_cap = (int)(per < kCacheMax ? per : kCacheMax);
         const size_t dyn = sizeof(uint32_t) * (size_t)cache_cap;
         static bool attr_done[64] = {};
         int devi = 0;
@@ -482,7 +533,19 @@ int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data,
             JABD_CUDA(cudaFuncSetAttribute(mbl_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(uint32_t) * kCacheMax)));
             if (devi >= 0 && devi < 64) attr_done[devi] = true;
         }
-        mbl_forward_kernel<<<(unsigned)B, kLossThreads, dyn, st>>>(a, cache_cap);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)B * kLossCluster);
+        cfg.blockDim = dim3(kLossThreads);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kLossCluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        JABD_CUDA(cudaLaunchKernelEx(&cfg, mbl_forward_kernel, a, cache_cap));
         JABD_LAUNCH_CHECK("mbl_forward_kernel");
     }
     mbl_finalize_kernel<<<1, 32, 0, st>>>(ws, (B > 0 && P > 0) ? B : 0, losses, norms);

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_k
         long long next = atomicAdd(&ws.ctl[1], 1);
         for (int k = 0;; ++k) {
             const int slot = k % kStages;
-            if (k >= kStages) mbar_wait(&s.empty[slot], (uint32_t)((k / kStages - 1) & 1));
+            if (k >= kStages) mbar_wait_relaxed(&s.empty[slot], (uint32_t)((k / kStages - 1) & 1));
             ItemMeta m;
             m.tile = -1; m.image = m.c0 = m.n = m.rec0 = m.pad0 = m.pad1 = m.pad2 = 0;
             if (item >= n_items) { // queue drained: publish the sentinel and stop
