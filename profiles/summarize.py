@@ -56,6 +56,14 @@ def launches():
         f.write("%-60s %8s %12s %10s %7s\n" % ("kernel", "launches", "total_us", "avg_us", "share"))
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-60s %8d %12.1f %10.2f %6.1f%%\n" % (k[:60], n, t / 1e3, t / n / 1e3, 100 * t / tot))
+        # the command also replays per-phase graphs (prep alone, prep+match, encode alone), so launch COUNTS differ per kernel;
+        # one step = one launch of each of the three kernels: shares of a step from the per-launch averages
+        step = [(k, agg[k][1] / agg[k][0]) for k in ("assign_prep_kernel", "assign_match_kernel", "match_encode_kernel") if k in agg]
+        if len(step) == 3:
+            st = sum(v for _, v in step)
+            f.write("\n# share of one step (avg per-launch time of its three kernels; bench.py's live phases are in <tag>_bench.json 'phases'):\n")
+            for k, v in step:
+                f.write("#   %-24s %6.2f us  %5.1f%%\n" % (k, v / 1e3, 100 * v / st))
     print("wrote", tag + "_launches_summary.txt")
 
 

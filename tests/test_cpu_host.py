@@ -44,6 +44,7 @@ def test_library_is_sm100a_with_tma(lib):
     assert "sm_100a" in sass
     assert "UBLKCP" in sass and "SYNCS" in sass           # cp.async.bulk + mbarrier in the matching kernel
     assert "REDUX" in sass                                # warp argmax
+    assert "UCGABAR_ARV" in sass and "UCGABAR_WAIT" in sass   # thread-block cluster barrier (loss forward, DSMEM histograms)
 
 
 def test_host_side_validation_without_gpu(lib):
