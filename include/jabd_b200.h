@@ -259,7 +259,9 @@ JABD_API int jabd_detect(const float *loc, const float *conf, const float *landm
                          int keep_cap, float *dets, int *counts, int *keep_idx, void *workspace, size_t workspace_bytes,
                          jabd_stream_t stream);
 /* Same with HOST buffers: loc/conf/landm in, dets/counts/keep_idx out; priors stay on the device.
- * Synchronises `stream` before returning. */
+ * Synchronises `stream` before returning.  Pinned (page-locked, hence device-mapped) loc_host / landm_host are not
+ * uploaded: the kernel reads the loc rows of the <= pre_nms_topk candidates and the landmark rows of the <= keep_cap kept
+ * detections directly from host memory (conf is always copied: every score is scanned); pageable memory is copied. */
 JABD_API size_t jabd_detect_host_scratch_bytes(int B, int64_t P, int keep_cap, int with_landm);
 JABD_API int jabd_detect_host(const float *loc_host, const float *conf_host, const float *landm_host,
                               const float *priors_dev, int B, int64_t P, float var0, float var1, float conf_thres,

@@ -355,6 +355,14 @@ class HostDetect(object):
         sl = self.slots[k]
         sl["done"].synchronize()
         v0, v1 = _tensor.variances_of(variances)
+        # pinned loc / landmarks are not uploaded: the kernel reads the <= pre_nms_topk candidate rows (16 B) and the
+        # <= keep_cap kept rows (40 B) from host memory
+        topk = int(pre_nms_topk) if pre_nms_topk else 0
+        loc_bytes = self.B * topk * 16 if (topk > 0 and self.P >= 6 * topk and loc.is_pinned()) else self.B * self.P * 16
+        lm_bytes = 0
+        if self.with_landm and landm is not None:
+            lm_bytes = self.B * self.keep_cap * 40 if landm.is_pinned() else self.B * self.P * 40
+        self.last_h2d = self.B * self.P * 8 + loc_bytes + lm_bytes
         with torch.cuda.device(self.dev):
             _lib.call("jabd_detect_host_async", ptr(loc), ptr(conf), ptr(landm if self.with_landm else None), ptr(self.pri),
                       self.B, self.P, v0, v1, float(conf_thres), THRESH_GT if strict else THRESH_GE,

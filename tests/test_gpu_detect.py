@@ -228,8 +228,12 @@ def test_detect_cfg3_batch_vs_oracle(mods, gen):
     d1, c1, k1 = mods["batched"].detect(loc[2:3].cuda(), conf[2:3].cuda(), landm[2:3].cuda(), pri, VAR)
     assert torch.equal(d1[0], dets[2]) and torch.equal(k1[0], kidx[2]) and int(c1[0]) == int(counts[2])
     h = mods["batched"].HostDetect(pri, B)
-    hd, hc, hk = h(loc.contiguous(), conf.contiguous(), landm.contiguous())
+    hd, hc, hk = h(loc.contiguous(), conf.contiguous(), landm.contiguous())                  # pageable landmarks: copied
     assert torch.equal(hd, dets.cpu()) and torch.equal(hc, counts.cpu()) and torch.equal(hk, kidx.cpu())
+    full_h2d = h.last_h2d
+    hd, hc, hk = h(loc.pin_memory(), conf.pin_memory(), landm.contiguous().pin_memory())     # pinned: kept rows read in place
+    assert torch.equal(hd, dets.cpu()) and torch.equal(hc, counts.cpu()) and torch.equal(hk, kidx.cpu())
+    assert h.last_h2d < 0.45 * full_h2d
     # no landmarks, >= threshold, uncapped top-k and keep
     d2, c2, k2 = mods["batched"].detect(loc[:1].cuda(), conf[:1].cuda(), None, pri, VAR, conf_thres=0.5, strict=False,
                                         pre_nms_topk=0, nms_thres=0.3, keep_topk=0)
