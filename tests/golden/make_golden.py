@@ -390,8 +390,53 @@ def check(R):
         r3 = tp.suppress(det, 0.5, 0.3)
         if len(r1) != len(r2) or (len(r1) and not (np.array_equal(r1, r2) and np.array_equal(r1, r3))):
             print("non_max_suppression MISMATCH", trial); n_bad += 1
+    n_bad += check_next_rows(R)
     print("fuzz stats:", stats)
     print("CHECK", "FAILED (%d)" % n_bad if n_bad else "OK")
+    return n_bad
+
+
+def check_next_rows(R):
+    """Fuzz of the SURVEY 8(f) oracles against the live reference: WIDER AP evaluation (utils_map), IoU-family overlaps
+    and IouLoss gradients, DIoU-NMS."""
+    from oracle import oracle as orc
+    from oracle import torch_port as tp
+    from oracle import wider_eval as ow
+    _, _, r_bu, ub, _, diou = R
+    sys.path.insert(0, REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import utils.utils_map as r_map
+    sys.path.remove(REF)
+    n_bad = 0
+    for trial in range(60):
+        gt, keeps, pred = synth.make_eval_image(9, trial, count=(None if trial % 5 else 200))
+        if len(gt) == 0 or len(pred) == 0:
+            continue
+        keep = keeps[trial % 3]
+        for thr in (0.4, 0.5):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rec, prop = r_map.image_eval(pred, gt, keep.astype(np.float64), thr)
+            o_rec, o_prop = ow.image_eval(pred, gt, keep, thr)
+            info = r_map.img_pr_info(200, pred, prop, rec)
+            if not (np.array_equal(rec, o_rec) and np.array_equal(prop, o_prop) and
+                    np.array_equal(info, ow.img_pr_info(200, pred, o_prop, o_rec))):
+                print("WIDER EVAL MISMATCH", trial, thr); n_bad += 1
+    rng = np.random.default_rng(4242)
+    for trial in range(30):
+        n = int(rng.integers(1, 400))
+        a, b = family_boxes(n=max(n, 64), seed=1000 + trial)
+        a, b = torch.from_numpy(a[:n]), torch.from_numpy(b[:n])
+        for kind in ("iou", "giou", "diou", "ciou"):
+            ref = getattr(r_bu, "bbox_overlaps_" + kind)(a, b).numpy()
+            if not np.array_equal(ref, tp.overlaps_family(a, b, kind).numpy(), equal_nan=True):
+                print("OVERLAPS MISMATCH", kind, trial); n_bad += 1
+        bx = torch.from_numpy(np.ascontiguousarray(b.numpy()))
+        sc = torch.from_numpy(rng.permutation(n).astype(np.float32) / n)          # unique scores: one sort order
+        for (ov, tk, beta) in ((0.5, 200, 1.0), (0.3, n, 1.0)):
+            k_ref, c_ref = ub.diounms(bx, sc, ov, tk, beta)
+            k_o, c_o = orc.diounms(bx.numpy(), sc.numpy(), ov, tk, beta)
+            if c_ref != c_o or not np.array_equal(k_ref.numpy()[:c_ref], k_o[:c_o]):
+                print("DIOUNMS MISMATCH", trial, ov, tk); n_bad += 1
     return n_bad
 
 
