@@ -79,18 +79,20 @@ def allgather_detections(dets, counts, group=None):
         return dets, counts
     dets = dets.contiguous()
     counts = counts.contiguous()
-    out_d = torch.empty((world * dets.shape[0],) + tuple(dets.shape[1:]), dtype=dets.dtype, device=dets.device)
-    out_c = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
-    if dets.is_cuda and dets.dtype == torch.float32 and counts.dtype == torch.int32:
+    if dets.dtype == torch.float32 and counts.dtype == torch.int32:
         # one collective instead of two (a 1.4 MB message is latency-bound on NVLink): the int32 counts travel bit-cast
         # as an extra float32 column of the flattened rows
         b = int(dets.shape[0])
         flat = torch.cat([dets.reshape(b, -1), counts.view(torch.float32).reshape(b, 1)], 1)
         gathered = torch.empty((world * b, flat.shape[1]), dtype=torch.float32, device=dets.device)
-        dist.all_gather_into_tensor(gathered, flat, group=group)
-        out_d = gathered[:, :-1].reshape((world * b,) + tuple(dets.shape[1:]))
-        out_c = gathered[:, -1].contiguous().view(torch.int32)
-    elif dets.is_cuda:
+        if dets.is_cuda:
+            dist.all_gather_into_tensor(gathered, flat, group=group)
+        else:
+            dist.all_gather(list(gathered.chunk(world, 0)), flat, group=group)
+        return gathered[:, :-1].reshape((world * b,) + tuple(dets.shape[1:])), gathered[:, -1].contiguous().view(torch.int32)
+    out_d = torch.empty((world * dets.shape[0],) + tuple(dets.shape[1:]), dtype=dets.dtype, device=dets.device)
+    out_c = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
+    if dets.is_cuda:
         dist.all_gather_into_tensor(out_d, dets, group=group)
         dist.all_gather_into_tensor(out_c, counts, group=group)
     else:

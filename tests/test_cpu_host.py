@@ -134,7 +134,17 @@ dets = torch.full((B_local, keep, 15), float(rank + 1))
 counts = torch.full((B_local,), rank + 3, dtype=torch.int32)
 d, c = sharding.allgather_detections(dets, counts)
 assert d.shape == (8, keep, 15) and (d[:4] == 1).all() and (d[4:] == 2).all()
-assert c.tolist() == [3] * 4 + [4] * 4
+assert c.tolist() == [3] * 4 + [4] * 4 and c.dtype == torch.int32
+# ragged counts and distinct rows survive the single packed collective bit for bit (counts travel bit-cast as a float column)
+g = torch.Generator().manual_seed(7 + rank)
+dets = torch.rand((B_local, keep, 15), generator=g)
+counts = torch.tensor([0, 6, 2, 2147483647 if rank else 5], dtype=torch.int32)
+d, c = sharding.allgather_detections(dets, counts)
+both = [torch.rand((B_local, keep, 15), generator=torch.Generator().manual_seed(7 + r)) for r in range(2)]
+assert torch.equal(d, torch.cat(both, 0)) and c.tolist() == [0, 6, 2, 5, 0, 6, 2, 2147483647]
+# other dtypes fall back to two collectives
+d64, c64 = sharding.allgather_detections(dets.double(), counts.long())
+assert torch.equal(d64, torch.cat(both, 0).double()) and c64.tolist() == c.tolist()
 dist.destroy_process_group()
 print("ok", rank)
 """
