@@ -141,3 +141,38 @@ def test_multibox_loss_aux_and_edge_cases(mods):
     ref_m = F.smooth_l1_loss(landm.double()[pos1], landm_t.double()[pos1], reduction="sum") / 153.0
     ref_c = F.cross_entropy(conf.double()[sel], pos[sel].long(), reduction="sum") / 163.0
     np.testing.assert_allclose([l.item(), c.item(), m.item()], [ref_l.item(), ref_c.item(), ref_m.item()], rtol=1e-5)
+
+
+def test_multibox_loss_ties_across_cluster_ranks(mods):
+    """The forward kernel splits every image over a 4-CTA cluster (contiguous prior ranges).  With all rank values tied the
+    mined negatives are the lowest non-positive indices (stable descending sort, R/nets/retinaface_training.py:270-281) -- a
+    set that crosses the CTA boundaries; P is not a multiple of 4 and the batch needs more than one wave of clusters."""
+    batched = mods["batched"]
+    dev = torch.device("cuda")
+    B, P = 40, 701
+    g = torch.Generator().manual_seed(11)
+    loc = torch.randn((B, P, 4), generator=g).to(dev)
+    landm = torch.randn((B, P, 10), generator=g).to(dev)
+    loc_t = torch.randn((B, P, 4), generator=g).to(dev)
+    landm_t = torch.randn((B, P, 10), generator=g).to(dev)
+    conf = torch.full((B, P, 2), 0.5, device=dev)
+    conf_t = torch.zeros((B, P), dtype=torch.int64, device=dev)
+    npos = [(b * 7) % 60 for b in range(B)]                      # 0..59 positives at the END of the prior range
+    for b in range(B):
+        if npos[b]:
+            conf_t[b, P - npos[b]:] = 1
+    # two images with a partial tie group instead: distinct values above a large tie plateau
+    conf[3, :300, 0] = torch.linspace(-3.0, -1.0, 300, device=dev)      # larger rank value than the plateau, all distinct
+    conf[5, 200:500, 0] = -2.0                                          # a second, higher plateau in the middle
+    l, c, m, mask, norms = batched.multibox_loss((loc, conf, landm), loc_t, conf_t, landm_t, 7, return_aux=True)
+    neg = ((mask >> 2) & 1).cpu().numpy()
+    cf = conf.cpu().double()
+    rank_val = torch.logsumexp(cf, 2) - cf[:, :, 0]
+    rank_val[conf_t.cpu() != 0] = 0
+    for b in range(B):
+        want = min(7 * npos[b], P - 1)
+        order = torch.sort(rank_val[b], descending=True, stable=True)[1][:want].numpy()
+        expect = np.zeros(P, np.uint8)
+        expect[order] = 1
+        assert np.array_equal(neg[b], expect), b
+    assert float(norms[0]) == float(max(sum(npos), 1))
