@@ -55,15 +55,20 @@ def shard_range(n_items, rank=None, world=None, weights=None):
     return b[rank], b[rank + 1]
 
 
-# per-image cost of target assignment in GT-equivalents: prep + encode take ~0.49 us per 640^2 image on a B200 and
-# matching ~8.1 ns per GT (profiles/r01_bench.json phases), so an image costs about as much as 60 extra GT
-IMAGE_COST_GT = 60
+# Cost model of one target-assignment call on a B200, fitted by profiles/cost_model_probe.py over batches of 16..48 images with
+# 5..300 GT each:  t [us] = 0.241*B + 0.00373*sum(G) + 0.0517*sum(ceil(G/64)) + 16.5.  In GT-equivalents an image costs 65
+# (prep + encode are per prior) and every started segment of 64 GT 14 (one work item per prior tile).
+IMAGE_COST_GT = 65
+SEGMENT_COST_GT = 14
+SEGMENT_GT = 64
 
 
-def local_targets(targets, rank=None, world=None, balance=True, image_cost=IMAGE_COST_GT):
+def local_targets(targets, rank=None, world=None, balance=True, image_cost=IMAGE_COST_GT, segment_cost=SEGMENT_COST_GT):
     """This rank's slice of a list of per-image ``[G_i,15]`` targets (+ its global image range).  ``balance``: contiguous
-    shards of equal estimated cost ``sum(G_i + image_cost)`` instead of equal image counts."""
-    weights = [int(t.shape[0]) + image_cost for t in targets] if balance else None
+    shards of equal estimated cost ``sum(G_i + segment_cost * ceil(G_i / 64) + image_cost)`` instead of equal image counts."""
+    weights = None
+    if balance:
+        weights = [int(t.shape[0]) + segment_cost * ((int(t.shape[0]) + SEGMENT_GT - 1) // SEGMENT_GT) + image_cost for t in targets]
     lo, hi = shard_range(len(targets), rank, world, weights)
     return targets[lo:hi], (lo, hi)
 
