@@ -204,16 +204,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- workload: SETS distinct batches per rank, all resident in HBM before timing
+    # ---- workload: SETS distinct batches, all resident in HBM before timing
     pri = anchors.Anchors(config.cfg_mnet, image_size=IMAGE).get_anchors()
     P = int(pri.shape[0])
     sets = []
     from jabd_b200 import sharding
     for s in range(SETS):
-        # step s%SETS processes the global batch of world*BATCH images [s*world*BATCH, (s+1)*world*BATCH); every rank
-        # generates the (cheap, seeded) GT of the whole batch and keeps its contiguous shard, cut so that the ranks'
-        # GT counts -- not their image counts -- are balanced (sharding.shard_bounds; cost ~ sum(G))
-        tg_all = synth.make_gt_batch(2, world * BATCH, IMAGE, first_image=s * world * BATCH)
+        # step s%SETS processes a global batch of world*BATCH images; every rank generates the (cheap, seeded) GT of the
+        # whole batch and keeps its contiguous shard, cut by estimated cost, not image count (sharding.local_targets)
+        # weak scaling compares identical per-GPU work: the global batch of step s is the N=1 batch of step s once per rank
+        # (world * BATCH images), cut into contiguous shards of equal estimated cost by the same code a real run uses
+        tg_all = synth.make_gt_batch(2, BATCH, IMAGE, first_image=s * BATCH) * world
         tg, (lo, hi) = sharding.local_targets(tg_all, rank, world, balance=True)
         nb = len(tg)
         gt, offs, offs_host = batched.pack_targets([t for t in tg], dev)
@@ -250,6 +251,8 @@ def main():
             assign(s)
         graphs.append(g)
 
+    last_rank_ms = [None]
+
     def timed_loop(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -259,7 +262,16 @@ def main():
             fn(k)
         e1.record()
         barrier()
-        return max_over_ranks(e0.elapsed_time(e1)), (t0, time.time())
+        last_rank_ms[0] = e0.elapsed_time(e1)
+        return max_over_ranks(last_rank_ms[0]), (t0, time.time())
+
+    def per_rank(x):
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = torch.empty((world,), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.tolist()]
 
     sampler = ClockSampler(local) if rank == 0 else None
     windows = []
@@ -267,6 +279,9 @@ def main():
         graphs[k % SETS].replay()
     ms, win = timed_loop(lambda k: graphs[k % SETS].replay(), K)
     windows.append(win)
+    rank_ms = per_rank(last_rank_ms[0])                     # every rank's own device time for the K steps
+    rank_images = per_rank(float(sum(s_["B"] for s_ in sets)) / SETS)
+    rank_gt = per_rank(float(sum(s_["sumG"] for s_ in sets)) / SETS)
     value = world * BATCH * K / (ms / 1e3)
     # hold the same load for ~1.5 s so that the 50 ms clock sampler sees the GPU under this workload
     hold = max(int(1.5e3 / max(ms / K, 1e-3)), 1)
@@ -627,11 +642,14 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2 training target assignment (match+encode): batch %d/GPU at 640x640, %d priors, "
                                "1..300 GT/image (mean %.1f), threshold 0.35, variances [0.1,0.2]" % (BATCH, P, mean_g),
-                   "global_batch": world * BATCH, "image": list(IMAGE), "priors": P, "parallelism": "image-sharded x%d, no collective" % world,
+                   "global_batch": world * BATCH, "image": list(IMAGE), "priors": P, "parallelism": "image-sharded x%d, no collective; the global batch is the N=1 batch once per rank "
+                                  "(identical per-GPU work)" % world,
                    "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2), one CUDA graph each"
                          % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "phases": phases,
         "detect": detect_info, "loss": loss_info, "cfg5_eval": cfg5_info,
+        "per_rank": {"ms_per_step": [x / K for x in rank_ms], "images_per_step": rank_images, "gt_per_step": rank_gt,
+                     "note": "value uses the slowest rank; shards are cut by estimated cost (sharding.local_targets)"},
     }
     emit(line)
     return 0
