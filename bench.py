@@ -386,41 +386,44 @@ def main():
     ms_e2e, _ = timed_loop(e2e_step, n_e2e)
     e2e_value = world * BATCH * n_e2e / (ms_e2e / 1e3)
     ms_e2e_sync, _ = timed_loop(lambda k: host(host_sets[k % SETS]), n_e2e)   # same call, one batch at a time
-    # variant: targets stay on the GPU (what a training loop consumes), only the positives count comes back
+    # variant: the training flow -- GT rows from pinned host memory in, targets left in HBM for the loss (what
+    # MultiBoxLoss.forward does with them), the step's result read back = the per-image positive counts.  Same C-ABI call
+    # with JABD_ASSIGN_DEVICE_OUT, two slots.
+    host_dev = batched.HostAssign(pri, BATCH, max(sum(int(t.shape[0]) for t in hs) for hs in host_sets), device_out=True)
+    cnt_pin = [torch.empty((BATCH,), dtype=torch.int64).pin_memory() for _ in range(2)]
+    cnt_done = [torch.cuda.Event() for _ in range(2)]
+    pend_dev = []
+
+    def collect(k):
+        slot = pend_dev.pop(0)
+        cnt_done[slot].synchronize()
+
+    def e2e_device_out(k):
+        slot = host_dev.submit(host_sets[k % SETS])
+        st = host_dev.slot_stream(slot)
+        with torch.cuda.stream(st):
+            cnt_pin[slot].copy_((host_dev.slots[slot]["conf_t"] != 0).sum(1), non_blocking=True)
+            cnt_done[slot].record(st)
+        pend_dev.append(slot)
+        if len(pend_dev) > 1:
+            collect(k)
+        if k == n_e2e - 1:
+            collect(k)
+
+    for k in range(4):
+        e2e_device_out(k)
+    while pend_dev:
+        collect(0)
+    ms_e2e_dev, _ = timed_loop(e2e_device_out, n_e2e)
     dsets = []
-    for hs in host_sets:
+    for hs in host_sets[:1]:
         gt_d, offs_d, _ = batched.pack_targets(hs, dev)
         sg = int(gt_d.shape[0])
-        dsets.append(dict(gt=gt_d, offs=offs_d, sumG=sg, B=BATCH, pin=torch.cat(hs, 0).pin_memory(),
+        dsets.append(dict(gt=gt_d, offs=offs_d, sumG=sg, B=BATCH,
                           ws=_tensor.workspace(L.jabd_assign_workspace_bytes(BATCH, P, sg), dev),
                           loc=torch.empty((BATCH, P, 4), dtype=torch.float32, device=dev),
                           conf=torch.empty((BATCH, P), dtype=torch.int64, device=dev),
                           landm=torch.empty((BATCH, P, 10), dtype=torch.float32, device=dev)))
-    # two slots on two streams: while the host waits for step k-1's positive counts, step k's upload and kernels are queued
-    slots = [dict(stream=torch.cuda.Stream(dev), done=torch.cuda.Event(), pin_cnt=torch.empty((BATCH,), dtype=torch.int64).pin_memory())
-             for _ in range(2)]
-    pend_dev = []
-
-    def e2e_device_out(k):
-        s, sl = dsets[k % SETS], slots[k % 2]
-        sl["done"].synchronize()
-        with torch.cuda.stream(sl["stream"]):
-            s["gt"].copy_(s["pin"], non_blocking=True)
-            assign(s, st=sl["stream"])
-            sl["pin_cnt"].copy_((s["conf"] != 0).sum(1), non_blocking=True)
-            sl["done"].record(sl["stream"])
-        pend_dev.append(k % 2)
-        if len(pend_dev) > 1:
-            slots[pend_dev.pop(0)]["done"].synchronize()
-        if k == n_e2e - 1:
-            slots[pend_dev.pop(0)]["done"].synchronize()
-
-    for k in range(4):
-        e2e_device_out(k)
-    for sl in slots:
-        sl["done"].synchronize()
-    pend_dev.clear()
-    ms_e2e_dev, _ = timed_loop(e2e_device_out, n_e2e)
     e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host.last_h2d, "d2h_bytes_per_step": host.last_d2h,
            "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
            "api": "batched.HostAssign.submit/wait -> jabd_assign_host (JABD_ASSIGN_ASYNC, 2 slots): list of per-image GT "
@@ -429,9 +432,10 @@ def main():
            "synchronous_call": {"value": world * BATCH * n_e2e / (ms_e2e_sync / 1e3), "unit": "images/s",
                                 "ms_per_step": ms_e2e_sync / n_e2e, "note": "HostAssign(targets): one batch at a time"},
            "device_resident_targets": {"value": world * BATCH * n_e2e / (ms_e2e_dev / 1e3), "unit": "images/s",
-                                       "h2d_bytes_per_step": int(dsets[0]["pin"].numel() * 4), "d2h_bytes_per_step": BATCH * 8,
-                                       "note": "GT H2D + assign + per-image positive count D2H, two slots on two streams; targets stay in HBM "
-                                               "for the loss (what MultiBoxLoss.forward does with them)"}}
+                                       "h2d_bytes_per_step": host_dev.last_h2d, "d2h_bytes_per_step": BATCH * 8,
+                                       "note": "batched.HostAssign(device_out=True) -> jabd_assign_host(JABD_ASSIGN_DEVICE_OUT | ASYNC), two "
+                                               "slots: per-image GT tensors packed into pinned memory and copied in, targets stay in HBM "
+                                               "for the loss (what MultiBoxLoss.forward does with them), per-image positive counts read back"}}
 
     # ---- the whole MultiBoxLoss.forward + backward on the device (assign -> mining -> sums -> grads)
     loss_info = None

@@ -57,6 +57,9 @@ enum {
 #define JABD_ASSIGN_PREP_ONLY 2 /* jabd_assign_match only: launch the staging kernel alone (per-kernel timing) */
 #define JABD_ASSIGN_ASYNC 4 /* jabd_assign_host only: do not synchronise; host buffers must be pinned and the caller
                                synchronises `stream` (or an event recorded on it) before reading the outputs */
+#define JABD_ASSIGN_DEVICE_OUT 16 /* jabd_assign_host only: loc_t / conf_t / landm_t are DEVICE buffers -- the targets stay in
+                                     HBM for the loss (what MultiBoxLoss.forward does with them, R/nets/retinaface_training.py
+                                     :220-227); only gt / gt_off cross the bus */
 
 JABD_API int jabd_version(void);
 JABD_API const char *jabd_last_error(void);
@@ -127,7 +130,13 @@ JABD_API int jabd_assign_encode(const float *priors, int64_t P, const float *gt,
 /* Same call with HOST buffers (pageable or pinned): copies gt/gt_off in, runs jabd_assign, copies the
  * three target tensors out.  priors and the staging area stay on the device:
  * dev_scratch must hold jabd_assign_host_scratch_bytes().  Synchronises `stream` before returning unless
- * JABD_ASSIGN_ASYNC is set (two calls on two streams with two scratch areas then overlap copies and kernels). */
+ * JABD_ASSIGN_ASYNC is set (two calls on two streams with two scratch areas then overlap copies and kernels).
+ * With JABD_ASSIGN_DEVICE_OUT the three outputs are device pointers and nothing is copied back. */
+/* Host-only helper for the list-of-arrays form the reference's data loader yields (R/utils/dataloader.py:37-58, one [G_i,15]
+ * float32 array per image): copies the rows of B host arrays into one packed buffer and writes the B+1 offsets.
+ * Returns sum(G) or a negative code (capacity_rows too small, null pointer, negative count). */
+JABD_API int64_t jabd_pack_gt_rows(const float *const *rows, const int *counts, int B, float *gt_packed, int64_t capacity_rows,
+                                   int *gt_off);
 JABD_API size_t jabd_assign_host_scratch_bytes(int B, int64_t P, int64_t sumG, int with_landm);
 JABD_API int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, const int *gt_off_host, int B,
                               float threshold, float var0, float var1, int label_mode, int encode_mode, int flags,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "jabd_assign_match": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_sz, c_vp]),
     "jabd_assign_encode": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int,
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_pack_gt_rows": (c_i64, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     "jabd_assign_host_scratch_bytes": (c_sz, [c_int, c_i64, c_i64, c_int]),
     "jabd_assign_host": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_int, c_int, c_int,
                                  c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -22,6 +22,7 @@ __all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "d
 THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
 FLAG_DENSE = 1
 FLAG_ASYNC = 4
+FLAG_DEVICE_OUT = 16
 
 
 def pack_targets(targets, device):
@@ -253,25 +254,35 @@ class HostAssign(object):
     ``h(targets)`` is synchronous.  ``submit`` / ``wait`` expose the same call as a ``depth``-slot pipeline (one
     stream, scratch area and pinned output set per slot, ``JABD_ASSIGN_ASYNC``): while slot k's 34 MB of targets
     drain over PCIe, slot k+1's GT upload and kernels already run.  The tensors returned by ``wait(slot)`` stay
-    valid until that slot is submitted again."""
+    valid until that slot is submitted again.
 
-    def __init__(self, priors, B, max_sum_g, with_landm=True, device=None, depth=2):
+    ``device_out=True``: the three target tensors are CUDA tensors and stay in HBM (``JABD_ASSIGN_DEVICE_OUT``) -- the
+    training flow, where ``MultiBoxLoss`` consumes them on the device; only the GT rows cross the bus.  Work that
+    consumes them must be ordered after ``wait(slot)`` or enqueued on ``slot_stream(slot)``."""
+
+    def __init__(self, priors, B, max_sum_g, with_landm=True, device=None, depth=2, device_out=False):
         _tensor.require_cuda()
         self.dev = torch.device(device) if device is not None else _tensor.device_of(priors)
         self.pri = _tensor.to_dev(priors, self.dev)
         self.B, self.P, self.cap = int(B), int(self.pri.shape[0]), int(max_sum_g)
         self.with_landm = bool(with_landm)
+        self.device_out = bool(device_out)
         L = _lib.lib()
         nbytes = L.jabd_assign_host_scratch_bytes(self.B, self.P, self.cap, 1 if with_landm else 0)
+
+        def out(shape, dtype):
+            if self.device_out:
+                return torch.empty(shape, dtype=dtype, device=self.dev)
+            return torch.empty(shape, dtype=dtype).pin_memory()
         self.slots = []
         for _ in range(max(int(depth), 1)):
             self.slots.append(dict(
                 scratch=_tensor.workspace(nbytes, self.dev),
                 gt=torch.empty((self.cap, 15), dtype=torch.float32).pin_memory(),
                 off=torch.empty((self.B + 1,), dtype=torch.int32).pin_memory(),
-                loc_t=torch.empty((self.B, self.P, 4), dtype=torch.float32).pin_memory(),
-                conf_t=torch.empty((self.B, self.P), dtype=torch.int64).pin_memory(),
-                landm_t=torch.empty((self.B, self.P, 10), dtype=torch.float32).pin_memory() if with_landm else None,
+                loc_t=out((self.B, self.P, 4), torch.float32),
+                conf_t=out((self.B, self.P), torch.int64),
+                landm_t=out((self.B, self.P, 10), torch.float32) if with_landm else None,
                 stream=torch.cuda.Stream(self.dev), done=torch.cuda.Event()))
         self.next_slot = 0
         self.last_h2d = self.last_d2h = 0
@@ -284,25 +295,35 @@ class HostAssign(object):
         self.next_slot = (k + 1) % len(self.slots)
         sl = self.slots[k]
         sl["done"].synchronize()            # the slot's previous outputs may still be in flight
-        counts = [int(t.shape[0]) for t in targets]
-        total = sum(counts)
-        if total > self.cap:
-            raise ValueError("sumG exceeds the capacity this HostAssign was built for")
-        if total:
-            torch.cat([torch.as_tensor(t, dtype=torch.float32) for t in targets if t.shape[0]], 0, out=sl["gt"][:total])
         offs = sl["off"]
-        offs[0] = 0
-        torch.cumsum(torch.tensor(counts, dtype=torch.int32), 0, out=offs[1:])
+        # pack the per-image arrays into the slot's pinned buffer: one C call (jabd_pack_gt_rows) instead of torch.cat + cumsum
+        rows = (ctypes.c_void_p * self.B)()
+        counts = (ctypes.c_int * self.B)()
+        keep = []
+        f32 = torch.float32
+        for i, t in enumerate(targets):
+            if not (type(t) is torch.Tensor and t.dtype is f32 and not t.is_cuda and t.is_contiguous() and t.ndim == 2):
+                t = torch.as_tensor(t).detach().to("cpu", f32).reshape(-1, 15).contiguous()
+                keep.append(t)
+            rows[i] = t.data_ptr()
+            counts[i] = t.shape[0]
+        total = int(_lib.lib().jabd_pack_gt_rows(rows, counts, self.B, ptr(sl["gt"]), self.cap, ptr(offs)))
+        if total < 0:
+            _lib.check(int(total), "jabd_pack_gt_rows")
         v0, v1 = _tensor.variances_of(variances)
         with torch.cuda.device(self.dev):
             _lib.call("jabd_assign_host", ptr(self.pri), self.P, ptr(sl["gt"]), ptr(offs), self.B, float(threshold),
-                      v0, v1, int(label_mode), 1 if encode else 0, (FLAG_DENSE if dense else 0) | FLAG_ASYNC, ptr(sl["loc_t"]),
+                      v0, v1, int(label_mode), 1 if encode else 0,
+                      (FLAG_DENSE if dense else 0) | FLAG_ASYNC | (FLAG_DEVICE_OUT if self.device_out else 0), ptr(sl["loc_t"]),
                       ptr(sl["conf_t"]), ptr(sl["landm_t"]), ptr(sl["scratch"]), sl["scratch"].numel(),
                       ctypes.c_void_p(sl["stream"].cuda_stream))
             sl["done"].record(sl["stream"])
         self.last_h2d = total * 15 * 4 + (self.B + 1) * 4
-        self.last_d2h = self.B * self.P * (16 + 8 + (40 if self.with_landm else 0))
+        self.last_d2h = 0 if self.device_out else self.B * self.P * (16 + 8 + (40 if self.with_landm else 0))
         return k
+
+    def slot_stream(self, slot):
+        return self.slots[slot]["stream"]
 
     def wait(self, slot):
         sl = self.slots[slot]

@@ -35,6 +35,8 @@
 // disables culling and evaluates all P*G pairs; tests compare the two bit for bit.  If any prior, or any GT of an
 // image, is malformed (negative or non-finite area) that image takes a generic dense path with torch.max's
 // NaN-wins / first-index semantics.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace jabd {
@@ -645,6 +647,26 @@ int jabd_assign(const float *priors, int64_t P, const float *gt, const int *gt_o
                               workspace_bytes, stream);
 }
 
+int64_t jabd_pack_gt_rows(const float *const *rows, const int *counts, int B, float *gt_packed, int64_t capacity_rows, int *gt_off)
+{
+    JABD_REQUIRE(B >= 0 && gt_off && (B == 0 || (rows && counts)), JABD_EINVAL, "pack_gt_rows: null pointer or negative B");
+    int64_t total = 0;
+    gt_off[0] = 0;
+    for (int b = 0; b < B; ++b) {
+        const int g = counts[b];
+        JABD_REQUIRE(g >= 0 && (g == 0 || rows[b]), JABD_EINVAL, "pack_gt_rows: image %d has a negative count or a null array", b);
+        JABD_REQUIRE(total + g <= capacity_rows && total + g < (1ll << 31), JABD_EWORKSPACE,
+                     "pack_gt_rows: %lld rows exceed the packed buffer's capacity %lld", (long long)(total + g), (long long)capacity_rows);
+        if (g) {
+            JABD_REQUIRE(gt_packed != nullptr, JABD_EINVAL, "pack_gt_rows: gt_packed is null");
+            memcpy(gt_packed + total * JABD_GT_ROW, rows[b], sizeof(float) * JABD_GT_ROW * (size_t)g);
+        }
+        total += g;
+        gt_off[b + 1] = (int)total;
+    }
+    return total;
+}
+
 size_t jabd_assign_host_scratch_bytes(int B, int64_t P, int64_t sumG, int with_landm)
 {
     if (B < 0 || P < 0 || sumG < 0) return 0;
@@ -680,9 +702,15 @@ int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, c
     auto take = [&](size_t bytes) { char *q = base + off; off += round_up(bytes, 256); return q; };
     float *d_gt = reinterpret_cast<float *>(take(sizeof(float) * JABD_GT_ROW * (size_t)(sumG > 0 ? sumG : 1)));
     int *d_off = reinterpret_cast<int *>(take(sizeof(int) * (size_t)(B + 1)));
+    const bool dev_out = (flags & JABD_ASSIGN_DEVICE_OUT) != 0; // outputs are device buffers: written in place, not staged
     float *d_loc = reinterpret_cast<float *>(take(sizeof(float) * 4 * (size_t)B * P));
     int64_t *d_conf = reinterpret_cast<int64_t *>(take(sizeof(int64_t) * (size_t)B * P));
     float *d_landm = with_landm ? reinterpret_cast<float *>(take(sizeof(float) * 10 * (size_t)B * P)) : nullptr;
+    if (dev_out) {
+        d_loc = loc_t_host;
+        d_conf = conf_t_host;
+        d_landm = landm_t_host;
+    }
     void *d_ws = base + off;
     const size_t ws_bytes = dev_scratch_bytes - off;
     if (sumG > 0) JABD_CUDA(cudaMemcpyAsync(d_gt, gt_host, sizeof(float) * JABD_GT_ROW * (size_t)sumG, cudaMemcpyHostToDevice, st));
@@ -691,10 +719,12 @@ int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, c
                          flags & JABD_ASSIGN_DENSE, d_loc,
                          d_conf, d_landm, nullptr, nullptr, nullptr, nullptr, d_ws, ws_bytes, stream);
     if (rc != JABD_OK) return rc;
-    JABD_CUDA(cudaMemcpyAsync(loc_t_host, d_loc, sizeof(float) * 4 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
-    JABD_CUDA(cudaMemcpyAsync(conf_t_host, d_conf, sizeof(int64_t) * (size_t)B * P, cudaMemcpyDeviceToHost, st));
-    if (with_landm)
-        JABD_CUDA(cudaMemcpyAsync(landm_t_host, d_landm, sizeof(float) * 10 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
+    if (!dev_out) {
+        JABD_CUDA(cudaMemcpyAsync(loc_t_host, d_loc, sizeof(float) * 4 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
+        JABD_CUDA(cudaMemcpyAsync(conf_t_host, d_conf, sizeof(int64_t) * (size_t)B * P, cudaMemcpyDeviceToHost, st));
+        if (with_landm)
+            JABD_CUDA(cudaMemcpyAsync(landm_t_host, d_landm, sizeof(float) * 10 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
+    }
     if (!(flags & JABD_ASSIGN_ASYNC)) JABD_CUDA(cudaStreamSynchronize(st));
     return JABD_OK;
 }

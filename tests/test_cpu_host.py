@@ -73,6 +73,15 @@ def test_host_side_validation_without_gpu(lib):
     mis = vp(buf.ctypes.data + 4)
     assert L.jabd_decode(mis, mis, 4, 1, 0.1, 0.2, mis, None) == -2
     assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 7, 0, 0.3, 0, 4, mis, mis, None, 0, None) == -1
+    # host-only GT packing helper (list of per-image arrays -> packed rows + offsets)
+    import torch
+    ts = [torch.rand(3, 15), torch.zeros(0, 15), torch.rand(5, 15)]
+    rows = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in ts])
+    counts = (ctypes.c_int * 3)(3, 0, 5)
+    gt, off = torch.empty(10, 15), torch.empty(4, dtype=torch.int32)
+    assert L.jabd_pack_gt_rows(rows, counts, 3, vp(gt.data_ptr()), 10, vp(off.data_ptr())) == 8
+    assert off.tolist() == [0, 3, 3, 8] and torch.equal(gt[:8], torch.cat(ts, 0))
+    assert L.jabd_pack_gt_rows(rows, counts, 3, vp(gt.data_ptr()), 7, vp(off.data_ptr())) == -3 and "capacity" in lib.last_error()
     with pytest.raises(ValueError):
         lib.check(-2, "x")
     with pytest.raises(RuntimeError):

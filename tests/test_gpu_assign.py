@@ -312,6 +312,13 @@ def test_assign_host_entry(mods):
     assert not loc_t.is_cuda and torch.equal(loc_t, dev[0].cpu()) and torch.equal(conf_t, dev[1].cpu())
     assert torch.equal(landm_t, dev[2].cpu())
     assert h.last_d2h == 4 * 16800 * 64
+    # JABD_ASSIGN_DEVICE_OUT: same call, targets written to device tensors, pipelined over two slots
+    hd = mods["batched"].HostAssign(pri, 4, 2000, device_out=True)
+    slots = [hd.submit(targets), hd.submit(targets[::-1])]
+    a, b = hd.wait(slots[0]), hd.wait(slots[1])
+    assert a[0].is_cuda and hd.last_d2h == 0
+    assert torch.equal(a[0], dev[0]) and torch.equal(a[1], dev[1]) and torch.equal(a[2], dev[2])
+    assert torch.equal(b[1], dev[1].flip(0)) and torch.equal(b[0], dev[0].flip(0))
 
 
 def test_errors_are_loud(mods):
