@@ -389,6 +389,15 @@ def main():
     # variant: the training flow -- GT rows from pinned host memory in, targets left in HBM for the loss (what
     # MultiBoxLoss.forward does with them), the step's result read back = the per-image positive counts.  Same C-ABI call
     # with JABD_ASSIGN_DEVICE_OUT, two slots.
+    dsets = []
+    for hs in host_sets[:1]:
+        gt_d, offs_d, _ = batched.pack_targets(hs, dev)
+        sg = int(gt_d.shape[0])
+        dsets.append(dict(gt=gt_d, offs=offs_d, sumG=sg, B=BATCH,
+                          ws=_tensor.workspace(L.jabd_assign_workspace_bytes(BATCH, P, sg), dev),
+                          loc=torch.empty((BATCH, P, 4), dtype=torch.float32, device=dev),
+                          conf=torch.empty((BATCH, P), dtype=torch.int64, device=dev),
+                          landm=torch.empty((BATCH, P, 10), dtype=torch.float32, device=dev)))
     host_dev = batched.HostAssign(pri, BATCH, max(sum(int(t.shape[0]) for t in hs) for hs in host_sets), device_out=True)
     cnt_pin = [torch.empty((BATCH,), dtype=torch.int64).pin_memory() for _ in range(2)]
     cnt_done = [torch.cuda.Event() for _ in range(2)]
@@ -415,15 +424,6 @@ def main():
     while pend_dev:
         collect(0)
     ms_e2e_dev, _ = timed_loop(e2e_device_out, n_e2e)
-    dsets = []
-    for hs in host_sets[:1]:
-        gt_d, offs_d, _ = batched.pack_targets(hs, dev)
-        sg = int(gt_d.shape[0])
-        dsets.append(dict(gt=gt_d, offs=offs_d, sumG=sg, B=BATCH,
-                          ws=_tensor.workspace(L.jabd_assign_workspace_bytes(BATCH, P, sg), dev),
-                          loc=torch.empty((BATCH, P, 4), dtype=torch.float32, device=dev),
-                          conf=torch.empty((BATCH, P), dtype=torch.int64, device=dev),
-                          landm=torch.empty((BATCH, P, 10), dtype=torch.float32, device=dev)))
     e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host.last_h2d, "d2h_bytes_per_step": host.last_d2h,
            "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
            "api": "batched.HostAssign.submit/wait -> jabd_assign_host (JABD_ASSIGN_ASYNC, 2 slots): list of per-image GT "
