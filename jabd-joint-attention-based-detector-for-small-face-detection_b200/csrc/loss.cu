@@ -28,13 +28,14 @@ namespace cg = cooperative_groups;
 
 constexpr int kLossThreads = 1024;
 constexpr int kLossBins = 2048;
+constexpr int kMaxParts = 148 * 8; // CTAs of mbl_max_kernel
 #ifndef JABD_LOSS_CLUSTER
 #define JABD_LOSS_CLUSTER 4
 #endif
 constexpr int kLossCluster = JABD_LOSS_CLUSTER; // CTAs (SMs) per image: a thread-block cluster whose histograms meet in distributed shared memory
 
 struct LossWs {
-    unsigned *xmax;   // [1] ordered bits of max(conf_data)
+    unsigned *xmax;   // [kMaxParts] ordered bits of max(conf_data) per CTA of mbl_max_kernel (no memset, no atomics)
     double *partial;  // [B*kLossCluster,4] sum_l, sum_c, sum_landm, (unused): one row per CTA
     int *counts;      // [B,2] num_pos, num_pos1
 };
@@ -48,7 +49,7 @@ static size_t loss_ws_layout(int B, LossWs *w, char *base)
         return o;
     };
     const size_t nb = (size_t)(B > 0 ? B : 1);
-    size_t o_x = take(sizeof(unsigned) * 4);
+    size_t o_x = take(sizeof(unsigned) * kMaxParts);
     size_t o_p = take(sizeof(double) * 4 * nb * kLossCluster);
     size_t o_c = take(sizeof(int) * 2 * nb);
     if (w) {
@@ -79,13 +80,20 @@ __device__ __forceinline__ uint32_t rank_bits(const LossFwdArgs &a, const uint32
 
 __global__ void __launch_bounds__(256) mbl_max_kernel(const float *__restrict__ x, long long n, unsigned *out)
 {
+    __shared__ unsigned s_m[8];
     unsigned m = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const unsigned u = ord_of(__ldg(x + i));
         m = u > m ? u : m;
     }
     m = __reduce_max_sync(kFull, m);
-    if (lane_id() == 0 && m) atomicMax(out, m);
+    if (lane_id() == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned r = 0;
+        for (int w = 0; w < 8; ++w) r = s_m[w] > r ? s_m[w] : r;
+        out[blockIdx.x] = r; // one partial maximum per CTA; mbl_forward_kernel reduces them
+    }
 }
 
 struct LossSmem {
@@ -185,7 +193,7 @@ __device__ __forceinline__ void cluster_merge_hist(LossSmem &sm, int nbins, cg::
     cluster.sync(); // nobody overwrites its local histogram while a neighbour still reads it
 }
 
-__global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArgs a, int cache_cap)
+__global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArgs a, int cache_cap, int n_parts)
 {
     extern __shared__ __align__(16) uint32_t s_rank[];
     __shared__ LossSmem sm;
@@ -199,7 +207,22 @@ __global__ void __launch_bounds__(kLossThreads, 1) mbl_forward_kernel(LossFwdArg
     const long long row0 = (long long)b * P;
     const long long per = (P + kLossCluster - 1) / kLossCluster;
     const long long p_lo = crank * per < P ? crank * per : P, p_hi = (p_lo + per) < P ? (p_lo + per) : P;
-    const float M = ord_inv(a.ws.xmax[0]);
+    // global maximum of conf_data: reduce mbl_max_kernel's per-CTA partials (<= kMaxParts of them)
+    {
+        unsigned m = 0;
+        for (int i = tid; i < n_parts; i += kLossThreads) { const unsigned u = a.ws.xmax[i]; m = u > m ? u : m; }
+        m = __reduce_max_sync(kFull, m);
+        if (lane == 0) sm.wsum[warp] = m;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned r = 0;
+            for (int w = 0; w < kLossThreads / 32; ++w) r = sm.wsum[w] > r ? sm.wsum[w] : r;
+            sm.found_bin = r;
+        }
+        __syncthreads();
+    }
+    const float M = ord_inv(sm.found_bin);
+    __syncthreads();
 
     // ---- pass 1: counts + top 11 bits of the rank value
     for (int i = tid; i < kLossBins; i += kLossThreads) sm.local[i] = 0;
@@ -500,10 +523,9 @@ int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data,
                      "multibox_loss: null input pointer");
         JABD_REQUIRE(aligned_to(loc_data, 16) && aligned_to(loc_t, 16) && aligned_to(conf_data, 8) && aligned_to(conf_t, 8),
                      JABD_EALIGN, "multibox_loss: loc needs 16-byte, conf 8-byte alignment");
-        JABD_CUDA(cudaMemsetAsync(ws.xmax, 0, sizeof(unsigned), st));
         const long long n = 2ll * B * P;
         long long grid = (n + 256 * 8 - 1) / (256 * 8);
-        grid = grid > 148 * 8 ? 148 * 8 : (grid < 1 ? 1 : grid);
+        grid = grid > kMaxParts ? kMaxParts : (grid < 1 ? 1 : grid);
         mbl_max_kernel<<<(unsigned)grid, 256, 0, st>>>(conf_data, n, ws.xmax);
         JABD_LAUNCH_CHECK("mbl_max_kernel");
         LossFwdArgs a;
@@ -545,7 +567,7 @@ int jabd_multibox_loss_forward_ex(const float *loc_data, const float *conf_data,
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        JABD_CUDA(cudaLaunchKernelEx(&cfg, mbl_forward_kernel, a, cache_cap));
+        JABD_CUDA(cudaLaunchKernelEx(&cfg, mbl_forward_kernel, a, cache_cap, (int)grid));
         JABD_LAUNCH_CHECK("mbl_forward_kernel");
     }
     mbl_finalize_kernel<<<1, 32, 0, st>>>(ws, (B > 0 && P > 0) ? B : 0, losses, norms);
