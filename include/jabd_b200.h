@@ -258,6 +258,11 @@ JABD_API int jabd_diounms(const float *boxes, int64_t box_seg_stride, int64_t bo
                           float beta1, int keep_cap, int *keep_idx, int *keep_count, void *workspace, size_t workspace_bytes,
                           jabd_stream_t stream);
 
+/* jabd_nms / jabd_diounms / jabd_detect run each image (segment) on a thread-block cluster of 1, 2, 4 or 8 CTAs -- one SM
+ * each -- picked per call as the widest cluster for which the whole batch is still co-resident.  This pins the width for
+ * tests and measurements (0 = automatic, the default); results do not depend on it. */
+JABD_API int jabd_debug_set_detect_cluster(int ctas_per_image);
+
 /* Fused inference post-processing for a batch (R/predict.py:167-181 composed per SURVEY D4):
  * class-1 score (conf[:,1]) -> threshold -> top-k -> decode of the candidates -> NMS -> first keep_cap rows
  * [x1 y1 x2 y2 score | decode_landm] (zero padded), prior indices (padding -1) and counts.

@@ -23,6 +23,7 @@ SIGNATURES = {
     "jabd_device_info": (c_int, [c_vp, c_vp, c_vp]),
     "jabd_selftest_div": (c_int, [ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
     "jabd_fp32_probe": (c_int, [c_int, c_int, c_vp, c_vp]),
+    "jabd_debug_set_detect_cluster": (c_int, [c_int]),
     "jabd_priors_count": (c_i64, [c_vp, c_vp, c_int, c_int, c_int]),
     "jabd_priors": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp]),
     "jabd_point_form": (c_int, [c_vp, c_i64, c_vp, c_vp]),

@@ -1,0 +1,42 @@
+"""Fused detect (jabd_detect) timed at every CTAs-per-image width of the thread-block-cluster kernel (1, 2, 4, 8 and the
+automatic choice) on the 640^2 x 32 and cfg3 (1024^2 x 16) clustered synthetic predictions, plus single-image calls --
+a development probe for DESIGN.md, not a bench line.  Usage: python profiles/detect_cluster_probe.py"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from jabd_b200 import _lib, anchors, batched, config, synth  # noqa: E402
+
+VAR = (0.1, 0.2)
+torch.cuda.set_device(0)
+for (size, B, gen) in ((640, 32, "B"), (1024, 16, "B"), (1024, 16, "A"), (640, 1, "B"), (1024, 1, "B"), (640, 64, "B"), (2048, 8, "B")):
+    pri = anchors.Anchors(config.cfg_mnet, image_size=(size, size)).get_anchors()
+    P = pri.shape[0]
+    ls, cs, ms = [], [], []
+    for i in range(B):
+        gt = synth.make_gt(3, i, (size, size), count=60)
+        l, c, m = synth.make_preds_clustered(3, i, pri, gt, VAR, device="cuda") if gen == "B" else synth.make_preds_random(3, i, P)
+        ls.append(l.cuda()); cs.append(c.cuda()); ms.append(m.cuda())
+    loc, conf, landm = torch.stack(ls).contiguous(), torch.stack(cs).contiguous(), torch.stack(ms).contiguous()
+    ref, line = None, []
+    for width in (1, 2, 4, 8, 0):
+        _lib.call("jabd_debug_set_detect_cluster", width)
+        for _ in range(3):
+            out = batched.detect(loc, conf, landm, pri, VAR)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            out = batched.detect(loc, conf, landm, pri, VAR)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = e0.elapsed_time(e1) / 20
+        if ref is None:
+            ref = out
+        assert all(torch.equal(a, b) for a, b in zip(out, ref)), width
+        line.append("C=%s %.3f ms (%.0f img/s)" % (width or "auto", ms_, B / ms_ * 1e3))
+    _lib.call("jabd_debug_set_detect_cluster", 0)
+    print("%dx%d B=%d gen %s kept %.0f: %s" % (size, size, B, gen, ref[1].float().mean().item(), "; ".join(line)), flush=True)

@@ -335,3 +335,78 @@ def test_nms_division_free_decision_equals_exact_and_oracle(mods, n):
             if not nonfinite:
                 rk, rc = orc.nms_ssd(b, s, ov, tk)
                 assert np.array_equal(out[0], rk[:rc]), (ov, tk)
+
+
+@pytest.fixture
+def cluster_width():
+    """Pins the CTAs-per-image width of the detect / NMS kernels; always back to automatic afterwards."""
+    from jabd_b200 import _lib
+
+    def set_width(c):
+        _lib.call("jabd_debug_set_detect_cluster", int(c))
+    yield set_width
+    set_width(0)
+
+
+def test_detect_cluster_widths_agree(mods, cluster_width):
+    """One image on a thread-block cluster of 1, 2, 4 or 8 CTAs (split decode + kept-list slices, masks exchanged through
+    distributed shared memory): keep lists, counts and rows are identical for every width and equal the oracle's; covers
+    several images per launch, a ragged last chunk, an empty image and the landmark-less output stage."""
+    orc, synth = mods["orc"], mods["synth"]
+    pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(640, 640)).get_anchors()
+    P = pri.shape[0]
+    B = 5
+    locs, confs, lms = [], [], []
+    for i in range(B):
+        gt = synth.make_gt(2, i, (640, 640), count=40 + 30 * i)
+        l, c, m = synth.make_preds_clustered(2, i, pri.cpu(), gt, VAR) if i % 2 == 0 else synth.make_preds_random(2, i, P)
+        locs.append(l); confs.append(c); lms.append(m)
+    loc, conf, landm = torch.stack(locs).cuda(), torch.stack(confs).cuda(), torch.stack(lms).cuda()
+    conf[3, :, 1] = 0.0                                          # nothing above the threshold in image 3
+    conf[3, :, 0] = 1.0
+    with pytest.raises(ValueError):
+        cluster_width(3)
+    ref = None
+    for width in (1, 2, 4, 8, 0):
+        cluster_width(width)
+        out = [mods["batched"].detect(loc, conf, landm, pri, VAR),                                   # cfg3 parameters
+               mods["batched"].detect(loc, conf, None, pri, VAR, conf_thres=0.3, strict=False, pre_nms_topk=1234,
+                                      nms_thres=0.3, keep_topk=97)]
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = out
+            boxes = mods["ub"].decode(loc, pri, VAR).cpu().numpy()
+            pn = pri.cpu().numpy()
+            for i in range(B):
+                e_d, e_i = orc.detect(loc[i].cpu().numpy(), conf[i].cpu().numpy(), landm[i].cpu().numpy(), pn, VAR, 0.02, True,
+                                      5000, 0.4, 750, boxes_override=boxes[i])
+                c = int(out[0][1][i])
+                assert c == len(e_i) and np.array_equal(out[0][2][i, :c].cpu().numpy(), e_i)
+                assert np.array_equal(out[0][0][i, :c].cpu().numpy(), e_d)
+            assert int(out[0][1][3]) == 0
+        else:
+            for (d, c, k), (rd, rc_, rk) in zip(out, ref):
+                assert torch.equal(c, rc_) and torch.equal(k, rk) and torch.equal(d, rd), width
+
+
+@pytest.mark.parametrize("width", [2, 8])
+def test_nms_cluster_multi_round_and_workspace_spill(mods, cluster_width, width):
+    """jabd_nms on a cluster: more candidates than one selection round (several decode exchanges) and more keeps than the
+    shared-memory kept cache (slices read back from the workspace copy each CTA writes itself); SSD-legacy order too."""
+    ops, orc = mods["ops"], mods["orc"]
+    rng = np.random.default_rng(23)
+    n = 15000
+    c = rng.random((n, 2), dtype=np.float32)
+    wh = 0.004 + 0.02 * rng.random((n, 2), dtype=np.float32)
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    s = rng.random(n, dtype=np.float32)
+    s[::5] = s[1]
+    cluster_width(width)
+    ref = orc.nms_tv(b, s, 0.4)
+    assert len(ref) > 1536
+    keep, cnt = ops.nms_indices(cuda(b), 4, cuda(s), 1, n, 0.0, ops.THRESH_NONE, 0, 0.4, ops.NMS_TV, n, torch.device("cuda", 0))
+    c_ = int(cnt.item())
+    assert c_ == len(ref) and np.array_equal(keep[:c_].cpu().numpy(), ref)
+    ref_s, cnt_s = orc.nms_ssd(b[:3000], s[:3000], 0.45, 200)
+    keep, count = mods["box_utils"].nms(cuda(b[:3000]), cuda(s[:3000]), 0.45, 200)
+    assert count == cnt_s and np.array_equal(keep.cpu().numpy(), ref_s)
