@@ -40,3 +40,30 @@ for (size, B, gen) in ((640, 32, "B"), (1024, 16, "B"), (1024, 16, "A"), (640, 1
         line.append("C=%s %.3f ms (%.0f img/s)" % (width or "auto", ms_, B / ms_ * 1e3))
     _lib.call("jabd_debug_set_detect_cluster", 0)
     print("%dx%d B=%d gen %s kept %.0f: %s" % (size, size, B, gen, ref[1].float().mean().item(), "; ".join(line)), flush=True)
+
+# host-buffer pipeline depth (HostDetect.submit / wait): 640^2 x 32 and cfg3
+for (size, B) in ((640, 32), (1024, 16)):
+    pri = anchors.Anchors(config.cfg_mnet, image_size=(size, size)).get_anchors()
+    P = pri.shape[0]
+    ls, cs, ms = [], [], []
+    for i in range(B):
+        gt = synth.make_gt(3, i, (size, size), count=60)
+        l, c, m = synth.make_preds_clustered(3, i, pri, gt, VAR, device="cuda")
+        ls.append(l.cpu()); cs.append(c.cpu()); ms.append(m.cpu())
+    lp, cp, mp = torch.stack(ls).contiguous().pin_memory(), torch.stack(cs).contiguous().pin_memory(), torch.stack(ms).contiguous().pin_memory()
+    for depth in (1, 2, 3, 4):
+        hd = batched.HostDetect(pri, B, depth=depth)
+        for _ in range(3):
+            hd(lp, cp, mp)
+        n, pend = 40, []
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
+        for k in range(n):
+            pend.append(hd.submit(lp, cp, mp))
+            if len(pend) >= depth:
+                hd.wait(pend.pop(0))
+        while pend:
+            hd.wait(pend.pop(0))
+        dt = (time.perf_counter() - t0) / n
+        print("host pipeline %dx%d B=%d depth %d: %.3f ms per batch (%.0f img/s), h2d %d B" % (size, size, B, depth, dt * 1e3, B / dt, hd.last_h2d), flush=True)
