@@ -503,18 +503,19 @@ def main():
                 out = batched.detect(loc_d, conf_d, lm_d, pr, VAR)
             n_d = 30
             ms_d, _ = timed_loop(lambda k: batched.detect(loc_d, conf_d, lm_d, pr, VAR), n_d)
-            hd = batched.HostDetect(pr, B)
+            hd = batched.HostDetect(pr, B, depth=3)
             lp, cp, mp = loc_h.pin_memory(), conf_h.pin_memory(), lm_h.pin_memory()
             for _ in range(2):
                 hd(lp, cp, mp)
             pend_d = []
 
-            def det_e2e(k):                 # two-slot pipeline, drained inside the timed region
+            def det_e2e(k):                 # three-slot pipeline (two batches in flight behind the one collected), drained inside the timed region
                 pend_d.append(hd.submit(lp, cp, mp))
-                if len(pend_d) > 1:
+                if len(pend_d) > 2:
                     hd.wait(pend_d.pop(0))
                 if k == n_d - 1:
-                    hd.wait(pend_d.pop(0))
+                    while pend_d:
+                        hd.wait(pend_d.pop(0))
             ms_dh, _ = timed_loop(det_e2e, n_d)
             detect_info[name] = {"images_per_s": world * B * n_d / (ms_d / 1e3), "ms_per_batch": ms_d / n_d,
                                  "e2e_images_per_s": world * B * n_d / (ms_dh / 1e3), "e2e_h2d_bytes": hd.last_h2d,

@@ -14,7 +14,7 @@ VAR = (0.1, 0.2)
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 L = _lib.lib()
-for (size, B, gen) in ((640, 32, "B"), (1024, 16, "B"), (1024, 16, "A")):
+for (size, B, gen) in ((640, 32, "B"), (640, 1, "B"), (1024, 16, "B"), (1024, 16, "A")):
     pri = anchors.Anchors(config.cfg_mnet, image_size=(size, size)).get_anchors()
     P = pri.shape[0]
     boxes, scores = [], []
@@ -32,7 +32,9 @@ for (size, B, gen) in ((640, 32, "B"), (1024, 16, "B"), (1024, 16, "A")):
     cnt = torch.empty((B,), dtype=torch.int32, device=dev)
     ws = _tensor.workspace(L.jabd_nms_workspace_bytes(B, P, keep_cap), dev)
     res = {}
-    for mode in (0, 256):
+    for mode, width in ((0, 1), (0, 2), (0, 0), (256, 0)):      # CTAs per image: 1, automatic
+        _lib.call("jabd_debug_set_detect_cluster", width)
+
         def run():
             _lib.call("jabd_nms", ptr(bx), P * 4, 4, ptr(sc), P, 1, B, P, 0.02, 2, 5000, 0.4, mode, keep_cap, ptr(keep), ptr(cnt),
                       ptr(ws), ws.numel(), _tensor.stream_of(dev))
@@ -45,16 +47,19 @@ for (size, B, gen) in ((640, 32, "B"), (1024, 16, "B"), (1024, 16, "A")):
             run()
         e1.record()
         torch.cuda.synchronize()
-        res[mode] = (e0.elapsed_time(e1) / 20, keep.clone(), cnt.clone())
+        res[(mode, width)] = (e0.elapsed_time(e1) / 20, keep.clone(), cnt.clone())
         if hasattr(L, "jabd_debug_detect_profile"):   # development build (make EXTRA=-DJABD_DET_PROFILE)
             import ctypes
-            prof = (ctypes.c_longlong * 8)()
+            prof = (ctypes.c_longlong * 16)()
             L.jabd_debug_detect_profile(prof, 1)
             run()
             L.jabd_debug_detect_profile(prof, 1)
-            print("   mode %d CTA0 cycles: select %d, decode %d, chunk query+triangle %d, chunk resolve %d, chunks %d; "
-                  "inside select: histogram passes %d, compaction %d, sort %d" %
-                  (mode, prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6], prof[7]))
-    assert torch.equal(res[0][1], res[256][1]) and torch.equal(res[0][2], res[256][2])
-    print("%dx%d B=%d gen %s: default %.3f ms, exact-div %.3f ms per batch; mean kept %.1f" % (size, size, B, gen, res[0][0], res[256][0],
-                                                                                   res[0][2].float().mean().item()))
+            ch = max(prof[15], 1)
+            print("   mode %d width %s CTA0 cycles: select %d (histogram passes %d, compaction %d, sort %d), decode %d; %d chunks, per chunk: "
+                  "query %d, wait for slowest warp %d, cluster exchange %d, resolve %d, wait for next triangle %d; warp 1: next triangle %d, look-ahead %d" %
+                  (mode, width or "auto", prof[0], prof[5], prof[6], prof[7], prof[1], prof[15], prof[8] // ch, prof[9] // ch,
+                   prof[10] // ch, prof[11] // ch, prof[12] // ch, prof[13] // ch, prof[14] // ch))
+    a, b, c = res[(0, 1)], res[(0, 0)], res[(256, 0)]
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(b[1], c[1]) and torch.equal(b[2], c[2])
+    print("%dx%d B=%d gen %s: one CTA per image %.3f ms, automatic cluster width %.3f ms, exact-div %.3f ms per batch; mean kept %.1f"
+          % (size, size, B, gen, a[0], b[0], c[0], b[2].float().mean().item()))
