@@ -51,7 +51,8 @@ for (size, B) in ((640, 32), (1024, 16)):
         l, c, m = synth.make_preds_clustered(3, i, pri, gt, VAR, device="cuda")
         ls.append(l.cpu()); cs.append(c.cpu()); ms.append(m.cpu())
     lp, cp, mp = torch.stack(ls).contiguous().pin_memory(), torch.stack(cs).contiguous().pin_memory(), torch.stack(ms).contiguous().pin_memory()
-    for depth in (1, 2, 3, 4):
+    for width, depth in ((1, 1), (1, 2), (1, 3), (0, 1), (0, 2), (0, 3), (1, 2), (0, 2)):
+        _lib.call("jabd_debug_set_detect_cluster", width)
         hd = batched.HostDetect(pri, B, depth=depth)
         for _ in range(3):
             hd(lp, cp, mp)
@@ -66,4 +67,5 @@ for (size, B) in ((640, 32), (1024, 16)):
         while pend:
             hd.wait(pend.pop(0))
         dt = (time.perf_counter() - t0) / n
-        print("host pipeline %dx%d B=%d depth %d: %.3f ms per batch (%.0f img/s), h2d %d B" % (size, size, B, depth, dt * 1e3, B / dt, hd.last_h2d), flush=True)
+        print("host pipeline %dx%d B=%d width %s depth %d: %.3f ms per batch (%.0f img/s), h2d %d B" % (size, size, B, width or "auto", depth, dt * 1e3, B / dt, hd.last_h2d), flush=True)
+_lib.call("jabd_debug_set_detect_cluster", 0)
