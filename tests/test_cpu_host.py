@@ -45,6 +45,12 @@ def test_library_is_sm100a_with_tma(lib):
     assert "UBLKCP" in sass and "SYNCS" in sass           # cp.async.bulk + mbarrier in the matching kernel
     assert "REDUX" in sass                                # warp argmax
     assert "UCGABAR_ARV" in sass and "UCGABAR_WAIT" in sass   # thread-block cluster barrier (loss forward, DSMEM histograms)
+    # the detect / NMS kernels are cluster kernels too: per-function check that the barrier and the flagged 8-byte
+    # distributed-shared-memory store of the mask exchange (st.relaxed.cluster -> ST.E.64.STRONG.GPU) are in their code
+    for fn in ("detect_kernel", "nms_kernel"):
+        body = sass.split("Function : ")
+        mine = [b for b in body if b.split("\n", 1)[0].find(fn) >= 0]
+        assert mine and all("UCGABAR_ARV" in b and "ST.E.64.STRONG" in b for b in mine), fn
 
 
 def test_host_side_validation_without_gpu(lib):
@@ -73,6 +79,9 @@ def test_host_side_validation_without_gpu(lib):
     mis = vp(buf.ctypes.data + 4)
     assert L.jabd_decode(mis, mis, 4, 1, 0.1, 0.2, mis, None) == -2
     assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 7, 0, 0.3, 0, 4, mis, mis, None, 0, None) == -1
+    # CTAs per image of the detect / NMS kernels: 0 (automatic), 1, 2, 4, 8 -- a host-side setting, no device call
+    assert L.jabd_debug_set_detect_cluster(3) == -1 and "CTAs per image" in lib.last_error()
+    assert L.jabd_debug_set_detect_cluster(2) == 0 and L.jabd_debug_set_detect_cluster(0) == 0
     # host-only GT packing helper (list of per-image arrays -> packed rows + offsets)
     import torch
     ts = [torch.rand(3, 15), torch.zeros(0, 15), torch.rand(5, 15)]
