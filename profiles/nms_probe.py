@@ -55,9 +55,9 @@ for (size, B, gen) in ((640, 32, "B"), (640, 1, "B"), (1024, 16, "B"), (1024, 16
             run()
             L.jabd_debug_detect_profile(prof, 1)
             ch = max(prof[15], 1)
-            print("   mode %d width %s CTA0 cycles: select %d (histogram passes %d, compaction %d, sort %d), decode %d; %d chunks, per chunk: "
+            print("   mode %d width %s CTA0 cycles: select %d (histogram passes %d, compaction %d, sort %d + run exchange %d + rank merge %d), decode %d; %d chunks, per chunk: "
                   "query %d, wait for slowest warp %d, cluster exchange %d, resolve %d, wait for next triangle %d; warp 1: next triangle %d, look-ahead %d" %
-                  (mode, width or "auto", prof[0], prof[5], prof[6], prof[7], prof[1], prof[15], prof[8] // ch, prof[9] // ch,
+                  (mode, width or "auto", prof[0], prof[5], prof[6], prof[2], prof[3], prof[4], prof[1], prof[15], prof[8] // ch, prof[9] // ch,
                    prof[10] // ch, prof[11] // ch, prof[12] // ch, prof[13] // ch, prof[14] // ch))
     a, b, c = res[(0, 1)], res[(0, 0)], res[(256, 0)]
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(b[1], c[1]) and torch.equal(b[2], c[2])
