@@ -179,3 +179,54 @@ def test_sharding_world_size_2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+# ---- numpy restatements of two pieces of device arithmetic in csrc/detect.cu (the claims the kernels rest on) ---------------
+def _ord_of(v):
+    """common.cuh ord_of(): order-preserving float32 -> uint32 (NaN largest, +0 == -0)."""
+    b = v.view(np.uint32).astype(np.uint64)
+    u = np.where(b & 0x80000000, (~b) & 0xFFFFFFFF, b | 0x80000000)
+    u = np.where(v == 0, 0x80000000, u)
+    return np.where(np.isnan(v), 0xFFFFFFFF, u).astype(np.uint64)
+
+
+def _fine_bin(u):
+    """detect.cu fine_bin(): 64 bins per octave over [2^-30, 4), clamped at both ends."""
+    b = (u >> 17).astype(np.int64) - ((0xC0800000 >> 17) - 2048)
+    return np.clip(b, 0, 2047)
+
+
+def test_fine_bin_is_monotone_and_resolves_probabilities():
+    rng = np.random.default_rng(5)
+    v = np.concatenate([rng.standard_normal(20000).astype(np.float32) * 3, rng.random(20000, dtype=np.float32),
+                        np.float32(2.0) ** rng.integers(-40, 10, 2000).astype(np.float32),
+                        np.array([0.0, -0.0, 1.0, 3.9999998, 4.0, 1e30, -1e30, np.inf, -np.inf, 2.0 ** -30, 2.0 ** -31], np.float32)])
+    v = np.sort(v)
+    assert _ord_of(np.array([4.0], np.float32))[0] == 0xC0800000
+    u = _ord_of(v)
+    assert (np.diff(u.astype(np.int64)) >= 0).all()                 # ord_of is order preserving
+    fb = _fine_bin(u)
+    assert (np.diff(fb) >= 0).all() and fb.min() == 0 and fb.max() == 2047   # monotone: "bins >= cut" is a score threshold
+    p = np.linspace(0.02, 0.999, 5000, dtype=np.float32)
+    fine, coarse = np.unique(_fine_bin(_ord_of(p))).size, np.unique(_ord_of(p) >> 21).size
+    assert fine >= 300 and coarse <= 24                             # what the float's top 11 bits leave of a probability
+    assert _fine_bin(_ord_of(np.array([2.0 ** -30, 3.9999998], np.float32))).tolist() == [0, 2047]
+
+
+def test_division_free_nms_decision_matches_the_quotient():
+    """suppresses_tv(): inter > fl(uni * fl(t(1+2^-20))) implies fl(inter/uni) > t and inter < fl(uni * fl(t(1-2^-20))) implies
+    fl(inter/uni) < t, for uni in [2^-60, 2^60] and t in [2^-20, 2^20] -- checked in float32 on values crowded around t*uni."""
+    rng = np.random.default_rng(11)
+    f32 = np.float32
+    for t in (f32(0.3), f32(0.4), f32(0.5), f32(0.45), f32(2.0 ** -20), f32(0.99999994), f32(1.0), f32(2.0 ** 20)):
+        c_hi, c_lo = f32(t * f32(1.0 + 2.0 ** -20)), f32(t * f32(1.0 - 2.0 ** -20))
+        uni = (f32(2.0) ** rng.uniform(-60, 60, 400000).astype(f32)).astype(f32)
+        uni = np.concatenate([uni, rng.random(400000, dtype=f32) * f32(2.0)])       # box unions of normalised coordinates
+        k = rng.integers(-64, 65, uni.size).astype(f32)
+        inter = (uni * t * (f32(1.0) + k * f32(2.0 ** -22))).astype(f32)            # within +-16 guard widths of the threshold
+        ok = (uni >= f32(2.0 ** -60)) & (uni <= f32(2.0 ** 60)) & np.isfinite(inter) & (inter > 0)
+        uni, inter = uni[ok], inter[ok]
+        q = (inter / uni).astype(f32)                                               # IEEE division, what the reference evaluates
+        yes, no = inter > (uni * c_hi).astype(f32), inter < (uni * c_lo).astype(f32)
+        assert yes.sum() > 1000 and no.sum() > 1000 and (~(yes | no)).sum() > 1000  # all three outcomes are exercised
+        assert (q[yes] > t).all() and (q[no] < t).all()
