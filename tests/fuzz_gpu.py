@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised GPU-vs-oracle comparison over many seeds (not collected by pytest; run on a GPU box):
 
-    python tests/fuzz_gpu.py [n_trials [assign,nms/topk,detect,loss,eval]]
+    python tests/fuzz_gpu.py [n_trials [assign,nms/topk,tieblock,detect,loss,eval]]
 
 Target assignment (ragged batches, duplicate / touching / tiny / out-of-image GT, both label and encode modes, culled and
 dense), top-k with ties, NMS (torchvision / SSD / DIoU semantics, capped and uncapped), the fused detect pipeline, the MultiBox
@@ -101,6 +101,32 @@ def fuzz_nms(rng, trial):
     assert int(cnt) == len(order) and np.array_equal(idx.cpu().numpy()[:len(order)], order), ("topk", trial, n, k)
 
 
+def fuzz_nms_tie_block(rng, trial):
+    """More than 8192 equal scores around the selection cut: the fine first histogram cannot isolate a small cut bin, so the
+    exact three-pass radix select + ordered compaction run -- on every cluster width (replicated there, after a shared
+    first pass)."""
+    from jabd_b200 import _lib
+    n = int(rng.integers(12000, 30000))
+    c = rng.random((n, 2), dtype=np.float32)
+    wh = np.exp(rng.uniform(np.log(0.004), np.log(0.05), (n, 2))).astype(np.float32)
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    s = rng.random(n, dtype=np.float32)
+    tie = rng.permutation(n)[: int(rng.integers(8500, min(n - 2000, 16000)))]
+    s[tie] = np.float32(rng.uniform(0.2, 0.8))
+    thr = float(rng.choice([0.3, 0.5]))
+    ref = orc.nms_tv(b, s, thr)
+    cb, cs = cuda(b), cuda(s)
+    try:
+        for width in (1, 2, 4, 8, 0):
+            _lib.call("jabd_debug_set_detect_cluster", width)
+            for cap in (n, 750):
+                keep, cnt = _ops.nms_indices(cb, 4, cs, 1, n, 0.0, _ops.THRESH_NONE, 0, thr, _ops.NMS_TV, cap, dev)
+                c_ = int(cnt.item())
+                assert c_ == min(len(ref), cap) and np.array_equal(keep[:c_].cpu().numpy(), ref[:cap]), ("tie block", trial, n, width, cap)
+    finally:
+        _lib.call("jabd_debug_set_detect_cluster", 0)
+
+
 def fuzz_detect(rng, trial):
     size = [(160, 160), (320, 320), (640, 640)][trial % 3]
     pri = anchors.cached_priors(config.cfg_mnet, size, dev)
@@ -163,7 +189,8 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
     rng = np.random.default_rng(20240611)
-    jobs = (("assign", fuzz_assign, n), ("nms/topk", fuzz_nms, n), ("detect", fuzz_detect, max(n // 2, 1)),
+    jobs = (("assign", fuzz_assign, n), ("nms/topk", fuzz_nms, n), ("tieblock", fuzz_nms_tie_block, max(n // 6, 1)),
+            ("detect", fuzz_detect, max(n // 2, 1)),
             ("loss", fuzz_loss, max(n // 2, 1)), ("eval", fuzz_eval, max(n // 3, 1)))
     for name, fn, count in jobs:
         if only and name not in only:
