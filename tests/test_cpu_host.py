@@ -230,3 +230,25 @@ def test_division_free_nms_decision_matches_the_quotient():
         yes, no = inter > (uni * c_hi).astype(f32), inter < (uni * c_lo).astype(f32)
         assert yes.sum() > 1000 and no.sum() > 1000 and (~(yes | no)).sum() > 1000  # all three outcomes are exercised
         assert (q[yes] > t).all() and (q[no] < t).all()
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """profiles/r01_bench*.json are what bench.py printed on the B200 box: every key of the driver's contract is there."""
+    import json
+    for name, n in (("r01_bench.json", 1), ("r01_bench_n2.json", 2), ("r01_bench_n8.json", 8)):
+        line = open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1]
+        d = json.loads(line)
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                  "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["unit"] == "images/s" and d["scaling"] == "weak" and d["higher_is_better"] is True
+        assert "workload" in d["config"] and "model" not in d["config"] and d["vs_baseline"] is None and d["dtype"] == "f32"
+        assert d["gpu_launches"] == 3 * d["steps"] and d["warmup"] >= 3
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_reference.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
