@@ -9,7 +9,11 @@
  *   - Every pointer is DEVICE memory on the current CUDA device unless the name ends in `_host`.
  *   - fp32 data, C-contiguous.  `conf_t` is int64 (torch.LongTensor, R/nets/retinaface_training.py:199).
  *   - The caller owns every buffer, including the workspace; the library never allocates or frees
- *     device memory, keeps no pointer after return and has no global mutable state.
+ *     device memory, keeps no pointer after return and has no global mutable state: every option is an
+ *     argument of the call it affects.  (Process-wide memo tables of *device properties* -- shared-memory opt-in
+ *     done, resident clusters per width -- are atomics and never depend on a call's arguments.)
+ *   - Test and bench hooks (division self-test, FP32 probe) are NOT part of this ABI: they live in
+ *     libjabd_b200_selftest.so / include/jabd_b200_selftest.h.
  *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises unless
  *     its comment says so.  Calls are re-entrant and may run concurrently on distinct streams.
  *   - Return 0 on success or a negative JABD_E* code; `jabd_last_error()` gives a thread-local message.
@@ -65,15 +69,6 @@ JABD_API int jabd_version(void);
 JABD_API const char *jabd_last_error(void);
 /* Fills SM count and compute capability of the current device.  Synchronous, host only. */
 JABD_API int jabd_device_info(int *sm_count, int *cc_major, int *cc_minor);
-
-/* Test hook: compares the library's shared-reciprocal IEEE division with the compiler's div.rn on n pseudo-random
- * operand pairs.  out[0] = number of mismatches (out[1] scratch), first_bad[4] = (a, d, got, expected). */
-JABD_API int jabd_selftest_div(uint64_t n, uint64_t seed, unsigned long long *out, float *first_bad, jabd_stream_t stream);
-
-/* Bench hook: dependency-free FMUL/FADD chains (no FMA, no memory traffic) on `ctas` CTAs of 256 threads;
- * ctas * 256 * 32 * iters fp32 operations.  The caller times it: this is the measured FP32-pipe peak that the
- * matching kernel's roofline is reported against. */
-JABD_API int jabd_fp32_probe(int ctas, int iters, float *sink_dev, jabd_stream_t stream);
 
 /* ---- P1: prior boxes.  Replaces Anchors.get_anchors / Anchors_eval.get_anchors (R/utils/anchors.py:9-42,
  * :43-79).  steps_host[n_levels]; min_sizes_host[sizes_off_host[n_levels]] grouped per level by
@@ -138,6 +133,9 @@ JABD_API int jabd_assign_encode(const float *priors, int64_t P, const float *gt,
 JABD_API int64_t jabd_pack_gt_rows(const float *const *rows, const int *counts, int B, float *gt_packed, int64_t capacity_rows,
                                    int *gt_off);
 JABD_API size_t jabd_assign_host_scratch_bytes(int B, int64_t P, int64_t sumG, int with_landm);
+/* offsets4 = {loc_t, conf_t, landm_t, total bytes}: the layout of the targets inside the staging area.  Host outputs that
+ * are three views of one block with these offsets are copied back with ONE D2H transfer instead of three. */
+JABD_API int jabd_assign_host_out_offsets(int B, int64_t P, int with_landm, size_t *offsets4);
 JABD_API int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, const int *gt_off_host, int B,
                               float threshold, float var0, float var1, int label_mode, int encode_mode, int flags,
                               float *loc_t_host, int64_t *conf_t_host, float *landm_t_host, void *dev_scratch,
@@ -234,9 +232,22 @@ JABD_API int jabd_wider_eval(const double *pred, const int *pred_off, const doub
  *               than 2^-20 (relative) away from the threshold is decided by comparing inter with thr*union,
  *               which provably gives the same decision (detect.cu, suppresses()); tests compare the two. */
 #define JABD_NMS_EXACT_DIV 256
+/* jabd_nms / jabd_diounms / jabd_detect run each image (segment) on a thread-block cluster of 1, 2, 4 or 8 CTAs -- one SM
+ * each -- picked per call as the widest cluster for which the whole batch is still co-resident.  A call may pin the width
+ * (tests, measurements; results do not depend on it): `| JABD_NMS_CLUSTER(c)` in nms_mode, `JABD_DET_CLUSTER(c)` in the
+ * flags of jabd_detect*; c = 0 (automatic, the default), 1, 2, 4 or 8. */
+#define JABD_NMS_CLUSTER(c) ((c) << 12)
+#define JABD_DET_CLUSTER(c) (c)
+/* Every jabd_nms / jabd_diounms / jabd_detect call leaves JABD_SEL_STATS ints per segment in its workspace at byte offset
+ * jabd_nms_stats_offset(S, keep_cap): [0] selection rounds (<= 6144 candidates each), [1] rounds that ran the exact
+ * three-pass radix select + ordered compaction (more than 8192 candidates at or above the cut bin, i.e. massive score ties),
+ * [2] candidates handed to NMS, [3] 32-wide NMS chunks processed.  jabd_topk writes the same row per segment to the start of
+ * its (optional) workspace.  Diagnostics only. */
+#define JABD_SEL_STATS 4
 
 /* Segmented top-k (K1; stable descending order, ties -> lower index).  scores[s*seg_stride + i*elem_stride],
- * i < N, for s < S segments; out_idx [S,K] i32 (padding -1), out_count [S]. */
+ * i < N, for s < S segments; out_idx [S,K] i32 (padding -1), out_count [S].  workspace: NULL, or
+ * jabd_topk_workspace_bytes() to receive the selection statistics (JABD_SEL_STATS ints per segment). */
 JABD_API size_t jabd_topk_workspace_bytes(int S, int64_t N, int K);
 JABD_API int jabd_topk(const float *scores, int64_t seg_stride, int64_t elem_stride, int S, int64_t N, float conf_thres,
                        int thresh_mode, int K, int *out_idx, int *out_count, void *workspace, size_t workspace_bytes,
@@ -246,6 +257,7 @@ JABD_API int jabd_topk(const float *scores, int64_t seg_stride, int64_t elem_str
  * scores[s*score_seg_stride + i*score_stride].  pre_nms_topk <= 0: uncapped.  keep_idx [S,keep_cap] i32 in
  * the reference's output order (padding -1), keep_count [S].  Only the first keep_cap keeps are produced. */
 JABD_API size_t jabd_nms_workspace_bytes(int S, int64_t N, int keep_cap);
+JABD_API size_t jabd_nms_stats_offset(int S, int keep_cap);
 JABD_API int jabd_nms(const float *boxes, int64_t box_seg_stride, int64_t box_stride, const float *scores,
                       int64_t score_seg_stride, int64_t score_stride, int S, int64_t N, float conf_thres, int thresh_mode,
                       int pre_nms_topk, double nms_thres, int nms_mode, int keep_cap, int *keep_idx, int *keep_count,
@@ -258,11 +270,6 @@ JABD_API int jabd_diounms(const float *boxes, int64_t box_seg_stride, int64_t bo
                           float beta1, int keep_cap, int *keep_idx, int *keep_count, void *workspace, size_t workspace_bytes,
                           jabd_stream_t stream);
 
-/* jabd_nms / jabd_diounms / jabd_detect run each image (segment) on a thread-block cluster of 1, 2, 4 or 8 CTAs -- one SM
- * each -- picked per call as the widest cluster for which the whole batch is still co-resident.  This pins the width for
- * tests and measurements (0 = automatic, the default); results do not depend on it. */
-JABD_API int jabd_debug_set_detect_cluster(int ctas_per_image);
-
 /* Fused inference post-processing for a batch (R/predict.py:167-181 composed per SURVEY D4):
  * class-1 score (conf[:,1]) -> threshold -> top-k -> decode of the candidates -> NMS -> first keep_cap rows
  * [x1 y1 x2 y2 score | decode_landm] (zero padded), prior indices (padding -1) and counts.
@@ -270,8 +277,8 @@ JABD_API int jabd_debug_set_detect_cluster(int ctas_per_image);
 JABD_API size_t jabd_detect_workspace_bytes(int B, int64_t P, int keep_cap);
 JABD_API int jabd_detect(const float *loc, const float *conf, const float *landm, const float *priors, int B, int64_t P,
                          float var0, float var1, float conf_thres, int thresh_mode, int pre_nms_topk, double nms_thres,
-                         int keep_cap, float *dets, int *counts, int *keep_idx, void *workspace, size_t workspace_bytes,
-                         jabd_stream_t stream);
+                         int keep_cap, int flags, float *dets, int *counts, int *keep_idx, void *workspace,
+                         size_t workspace_bytes, jabd_stream_t stream);
 /* Same with HOST buffers: loc/conf/landm in, dets/counts/keep_idx out; priors stay on the device.
  * Synchronises `stream` before returning.  Pinned (page-locked, hence device-mapped) loc_host / landm_host are not
  * uploaded: the kernel reads the loc rows of the <= pre_nms_topk candidates and the landmark rows of the <= keep_cap kept
@@ -279,16 +286,16 @@ JABD_API int jabd_detect(const float *loc, const float *conf, const float *landm
 JABD_API size_t jabd_detect_host_scratch_bytes(int B, int64_t P, int keep_cap, int with_landm);
 JABD_API int jabd_detect_host(const float *loc_host, const float *conf_host, const float *landm_host,
                               const float *priors_dev, int B, int64_t P, float var0, float var1, float conf_thres,
-                              int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap, float *dets_host,
-                              int *counts_host, int *keep_idx_host, void *dev_scratch, size_t dev_scratch_bytes,
-                              jabd_stream_t stream);
+                              int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap, int flags,
+                              float *dets_host, int *counts_host, int *keep_idx_host, void *dev_scratch,
+                              size_t dev_scratch_bytes, jabd_stream_t stream);
 /* Same without the final synchronisation: host buffers must be pinned; the caller waits on `stream` (or an event
  * recorded on it) before reading the outputs.  Two calls on two streams with two scratch areas overlap. */
 JABD_API int jabd_detect_host_async(const float *loc_host, const float *conf_host, const float *landm_host,
                               const float *priors_dev, int B, int64_t P, float var0, float var1, float conf_thres,
-                              int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap, float *dets_host,
-                              int *counts_host, int *keep_idx_host, void *dev_scratch, size_t dev_scratch_bytes,
-                              jabd_stream_t stream);
+                              int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap, int flags,
+                              float *dets_host, int *counts_host, int *keep_idx_host, void *dev_scratch,
+                              size_t dev_scratch_bytes, jabd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,9 +21,6 @@ SIGNATURES = {
     "jabd_version": (c_int, []),
     "jabd_last_error": (ctypes.c_char_p, []),
     "jabd_device_info": (c_int, [c_vp, c_vp, c_vp]),
-    "jabd_selftest_div": (c_int, [ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
-    "jabd_fp32_probe": (c_int, [c_int, c_int, c_vp, c_vp]),
-    "jabd_debug_set_detect_cluster": (c_int, [c_int]),
     "jabd_priors_count": (c_i64, [c_vp, c_vp, c_int, c_int, c_int]),
     "jabd_priors": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp]),
     "jabd_point_form": (c_int, [c_vp, c_i64, c_vp, c_vp]),
@@ -41,6 +38,7 @@ SIGNATURES = {
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_pack_gt_rows": (c_i64, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
     "jabd_assign_host_scratch_bytes": (c_sz, [c_int, c_i64, c_i64, c_int]),
+    "jabd_assign_host_out_offsets": (c_int, [c_int, c_i64, c_int, c_vp]),
     "jabd_assign_host": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_int, c_int, c_int,
                                  c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_correct_boxes": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
@@ -62,30 +60,42 @@ SIGNATURES = {
     "jabd_topk_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
     "jabd_topk": (c_int, [c_vp, c_i64, c_i64, c_int, c_i64, c_f32, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_nms_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
+    "jabd_nms_stats_offset": (c_sz, [c_int, c_int]),
     "jabd_nms": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_i64, c_f32, c_int, c_int, c_f64, c_int,
                          c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_diounms": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_int, c_i64, c_int, c_f64, c_f32, c_int, c_vp, c_vp, c_vp,
                              c_sz, c_vp]),
     "jabd_detect_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
-    "jabd_detect": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64, c_int,
+    "jabd_detect": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64, c_int, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_detect_host_scratch_bytes": (c_sz, [c_int, c_i64, c_int, c_int]),
     "jabd_detect_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64,
-                                 c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                 c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_detect_host_async": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64,
-                                       c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+                                       c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+}
+
+# libjabd_b200_selftest.so (include/jabd_b200_selftest.h): test / bench hooks, deliberately not in the product library
+SELFTEST_SO_PATH = os.path.join(_HERE, "libjabd_b200_selftest.so")
+SELFTEST_SIGNATURES = {
+    "jabd_selftest_div": (c_int, [ctypes.c_uint64, ctypes.c_uint64, c_vp, c_vp, c_vp]),
+    "jabd_selftest_fp32_probe": (c_int, [c_int, c_int, c_vp, c_vp]),
+    "jabd_selftest_last_error": (ctypes.c_char_p, []),
 }
 
 ERRORS = {-1: ValueError, -2: ValueError, -3: ValueError, -4: RuntimeError, -5: RuntimeError}
 
 _lib = None
+_selftest = None
 
 
 def build(force=False, verbose=False):
     """Compile ``libjabd_b200.so`` for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "jabd_b200.h"))
-    stale = force or not os.path.exists(SO_PATH) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "jabd_b200_selftest.h"))
+    outs = (SO_PATH, SELFTEST_SO_PATH)
+    stale = force or any(not os.path.exists(o) or any(os.path.getmtime(s) > os.path.getmtime(o) for s in srcs) for o in outs)
     if stale:
         cmd = ["make", "-C", CSRC, "-j4"] + ([] if verbose else ["-s"])
         if force:
@@ -109,6 +119,28 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def selftest_lib():
+    """The test / bench hook library (never needed by the operators)."""
+    global _selftest
+    if _selftest is None:
+        if not os.path.exists(SELFTEST_SO_PATH):
+            raise RuntimeError("libjabd_b200_selftest.so is missing at %s: run `make -C %s`" % (SELFTEST_SO_PATH, CSRC))
+        L = ctypes.CDLL(SELFTEST_SO_PATH)
+        for name, (res, args) in SELFTEST_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _selftest = L
+    return _selftest
+
+
+def selftest_call(name, *args):
+    L = selftest_lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise ERRORS.get(rc, RuntimeError)("%s failed (%d): %s" % (name, rc, L.jabd_selftest_last_error().decode("utf-8", "replace")))
 
 
 def last_error():

@@ -125,20 +125,24 @@ def match_one(threshold, truths, priors, variances, labels, landms, loc_t, conf_
 
 
 def nms_indices(boxes, box_stride, scores, score_stride, n, conf_thres, thresh_mode, pre_nms_topk, nms_thres, nms_mode,
-                keep_cap, dev):
-    """Single-segment ``jabd_nms``; returns (keep_idx i32 [keep_cap] CUDA, count i32 [1] CUDA)."""
+                keep_cap, dev, cluster=0, return_stats=False):
+    """Single-segment ``jabd_nms``; returns (keep_idx i32 [keep_cap] CUDA, count i32 [1] CUDA).  ``cluster``: CTAs per segment
+    (``JABD_NMS_CLUSTER``, 0 = automatic); ``return_stats`` adds the selection statistics ``[4]`` i32 (see jabd_b200.h)."""
     L = _lib.lib()
     keep = torch.empty((max(keep_cap, 1),), dtype=torch.int32, device=dev)
     count = torch.empty((1,), dtype=torch.int32, device=dev)
     ws = _tensor.workspace(L.jabd_nms_workspace_bytes(1, n, keep_cap), dev)
     with torch.cuda.device(dev):
         _lib.call("jabd_nms", ptr(boxes), 0, box_stride, ptr(scores), 0, score_stride, 1, n, float(conf_thres), thresh_mode,
-                  int(pre_nms_topk), float(nms_thres), nms_mode, keep_cap, ptr(keep), ptr(count), ptr(ws), ws.numel(),
-                  _tensor.stream_of(dev))
+                  int(pre_nms_topk), float(nms_thres), int(nms_mode) | (int(cluster) << 12), keep_cap, ptr(keep), ptr(count),
+                  ptr(ws), ws.numel(), _tensor.stream_of(dev))
+    if return_stats:
+        off = int(L.jabd_nms_stats_offset(1, keep_cap))
+        return keep, count, ws[off:off + 16].view(torch.int32)
     return keep, count
 
 
-def topk(scores, k, conf_thres=None, strict=True):
+def topk(scores, k, conf_thres=None, strict=True, return_stats=False):
     """Segmented top-k: scores [S,N] or [N]; stable descending order, ties -> lower index.
     Returns (idx [S,k] i32 padded with -1, count [S] i32)."""
     kind, dev = _tensor.kind_of(scores), _tensor.device_of(scores)
@@ -150,11 +154,14 @@ def topk(scores, k, conf_thres=None, strict=True):
     out = torch.empty((S, k), dtype=torch.int32, device=dev)
     cnt = torch.empty((S,), dtype=torch.int32, device=dev)
     mode = THRESH_NONE if conf_thres is None else (THRESH_GT if strict else THRESH_GE)
+    ws = _tensor.workspace(_lib.lib().jabd_topk_workspace_bytes(S, N, int(k)), dev) if return_stats else None
     with torch.cuda.device(dev):
-        _lib.call("jabd_topk", ptr(s), N, 1, S, N, float(conf_thres or 0.0), mode, int(k), ptr(out), ptr(cnt), ptr(None), 0,
-                  _tensor.stream_of(dev))
+        _lib.call("jabd_topk", ptr(s), N, 1, S, N, float(conf_thres or 0.0), mode, int(k), ptr(out), ptr(cnt), ptr(ws),
+                  ws.numel() if ws is not None else 0, _tensor.stream_of(dev))
     if squeeze:
         out, cnt = out[0], cnt[0]
+    if return_stats:
+        return _tensor.like(kind, out), _tensor.like(kind, cnt), ws[:16 * S].view(torch.int32).reshape(S, 4)
     return _tensor.like(kind, out), _tensor.like(kind, cnt)
 
 

@@ -36,7 +36,9 @@ def pack_targets(targets, device):
         offs_host = [int(v) for v in (offs_in.tolist() if hasattr(offs_in, "tolist") else list(offs_in))]
         offs = _tensor.to_dev(offs_in, device, torch.int32)
     else:
-        rows = list(targets)
+        # numpy arrays and torch tensors are used as they are; anything else that speaks DLPack is imported without a copy
+        rows = [t if isinstance(t, (np.ndarray, torch.Tensor)) else (torch.from_dlpack(t) if hasattr(t, "__dlpack__") else
+                                                                     torch.as_tensor(t)) for t in targets]
         offs_host = [0]
         for t in rows:
             if t.ndim != 2 or t.shape[1] != 15:
@@ -108,12 +110,14 @@ def assign_targets(priors, targets, threshold=0.35, variances=(0.1, 0.2), label_
 
 
 def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000,
-           nms_thres=0.4, keep_topk=750):
+           nms_thres=0.4, keep_topk=750, cluster=0, return_stats=False):
     """Fused decode -> class-1 score threshold -> top-k -> NMS -> keep for a batch.
 
     loc [B,P,4], conf [B,P,2] (softmax probabilities, R/nets/retinaface_eca_nonlocal.py:355-359),
     landm [B,P,10] or None, priors [P,4].  ``strict``: score > conf_thres (cfg3) else >= (R/utils/utils_bbox.py:266).
     Returns ``(dets [B,keep_topk,15] zero padded, counts [B] i32, keep_idx [B,keep_topk] i32, -1 padded)`` on the GPU.
+    ``cluster``: CTAs (SMs) per image, 0 = automatic (``JABD_DET_CLUSTER``; results do not depend on it).
+    ``return_stats`` adds the call's selection statistics ``[B,4]`` i32 (rounds, exact three-pass rounds, candidates, chunks).
     """
     dev = _tensor.device_of(loc, conf, priors)
     loc_d, conf_d, pri = _tensor.to_dev(loc, dev), _tensor.to_dev(conf, dev), _tensor.to_dev(priors, dev)
@@ -135,7 +139,10 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
     with torch.cuda.device(dev):
         _lib.call("jabd_detect", ptr(loc_d), ptr(conf_d), ptr(landm_d), ptr(pri), B, P, v0, v1, float(conf_thres),
                   THRESH_GT if strict else THRESH_GE, int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), keep_cap,
-                  ptr(dets), ptr(counts), ptr(keep_idx), ptr(ws), ws.numel(), _tensor.stream_of(dev))
+                  int(cluster), ptr(dets), ptr(counts), ptr(keep_idx), ptr(ws), ws.numel(), _tensor.stream_of(dev))
+    if return_stats:
+        off = int(L.jabd_nms_stats_offset(B, keep_cap))
+        return dets, counts, keep_idx, ws[off:off + 16 * B].view(torch.int32).reshape(B, 4)
     return dets, counts, keep_idx
 
 
@@ -258,7 +265,12 @@ class HostAssign(object):
 
     ``device_out=True``: the three target tensors are CUDA tensors and stay in HBM (``JABD_ASSIGN_DEVICE_OUT``) -- the
     training flow, where ``MultiBoxLoss`` consumes them on the device; only the GT rows cross the bus.  Work that
-    consumes them must be ordered after ``wait(slot)`` or enqueued on ``slot_stream(slot)``."""
+    consumes them must be ordered after ``wait(slot)`` or enqueued on ``slot_stream(slot)``.
+
+    The three host outputs of a slot are views of ONE pinned block laid out like the device staging area
+    (``jabd_assign_host_out_offsets``), which lets ``jabd_assign_host`` bring them back with a single D2H copy.
+    The slot streams are ordered after the stream that produced ``priors`` (constructor) -- submit never reads priors
+    before they are written."""
 
     def __init__(self, priors, B, max_sum_g, with_landm=True, device=None, depth=2, device_out=False):
         _tensor.require_cuda()
@@ -270,20 +282,31 @@ class HostAssign(object):
         L = _lib.lib()
         nbytes = L.jabd_assign_host_scratch_bytes(self.B, self.P, self.cap, 1 if with_landm else 0)
 
-        def out(shape, dtype):
+        offs = (ctypes.c_size_t * 4)()
+        L.jabd_assign_host_out_offsets(self.B, self.P, 1 if with_landm else 0, offs)
+        BP = self.B * self.P
+
+        def outputs():
             if self.device_out:
-                return torch.empty(shape, dtype=dtype, device=self.dev)
-            return torch.empty(shape, dtype=dtype).pin_memory()
+                return (torch.empty((self.B, self.P, 4), dtype=torch.float32, device=self.dev),
+                        torch.empty((self.B, self.P), dtype=torch.int64, device=self.dev),
+                        torch.empty((self.B, self.P, 10), dtype=torch.float32, device=self.dev) if with_landm else None, None)
+            block = torch.empty((int(offs[3]),), dtype=torch.uint8).pin_memory()
+            loc = block[int(offs[0]):int(offs[0]) + BP * 16].view(torch.float32).reshape(self.B, self.P, 4)
+            conf = block[int(offs[1]):int(offs[1]) + BP * 8].view(torch.int64).reshape(self.B, self.P)
+            lm = block[int(offs[2]):int(offs[2]) + BP * 40].view(torch.float32).reshape(self.B, self.P, 10) if with_landm else None
+            return loc, conf, lm, block
         self.slots = []
+        cur = torch.cuda.current_stream(self.dev)
         for _ in range(max(int(depth), 1)):
+            loc, conf, lm, block = outputs()
+            st = torch.cuda.Stream(self.dev)
+            st.wait_stream(cur)          # self.pri may still be in flight on the caller's stream (priors kernel / H2D copy)
             self.slots.append(dict(
                 scratch=_tensor.workspace(nbytes, self.dev),
                 gt=torch.empty((self.cap, 15), dtype=torch.float32).pin_memory(),
                 off=torch.empty((self.B + 1,), dtype=torch.int32).pin_memory(),
-                loc_t=out((self.B, self.P, 4), torch.float32),
-                conf_t=out((self.B, self.P), torch.int64),
-                landm_t=out((self.B, self.P, 10), torch.float32) if with_landm else None,
-                stream=torch.cuda.Stream(self.dev), done=torch.cuda.Event()))
+                loc_t=loc, conf_t=conf, landm_t=lm, block=block, stream=st, done=torch.cuda.Event()))
         self.next_slot = 0
         self.last_h2d = self.last_d2h = 0
 
@@ -302,8 +325,12 @@ class HostAssign(object):
         keep = []
         f32 = torch.float32
         for i, t in enumerate(targets):
-            if not (type(t) is torch.Tensor and t.dtype is f32 and not t.is_cuda and t.is_contiguous() and t.ndim == 2):
-                t = torch.as_tensor(t).detach().to("cpu", f32).reshape(-1, 15).contiguous()
+            if not (type(t) is torch.Tensor and t.dtype is f32 and not t.is_cuda and t.is_contiguous() and t.ndim == 2
+                    and t.shape[1] == 15):
+                t = torch.as_tensor(t).detach().to("cpu", f32)
+                if t.ndim != 2 or t.shape[1] != 15:      # jabd_pack_gt_rows copies 15 floats per row: anything else is an
+                    raise ValueError("each target must be [G, 15] (x1 y1 x2 y2, 10 landmark coords, label)")   # out-of-bounds read
+                t = t.contiguous()
                 keep.append(t)
             rows[i] = t.data_ptr()
             counts[i] = t.shape[0]
@@ -362,12 +389,19 @@ class HostDetect(object):
                                    counts=torch.empty((self.B,), dtype=torch.int32).pin_memory(),
                                    keep_idx=torch.empty((self.B, self.keep_cap), dtype=torch.int32).pin_memory(),
                                    stream=torch.cuda.Stream(self.dev), done=torch.cuda.Event()))
+        cur = torch.cuda.current_stream(self.dev)
+        for sl in self.slots:
+            sl["stream"].wait_stream(cur)   # self.pri may still be in flight on the caller's stream
         self.next_slot = 0
         self.last_h2d = self.B * self.P * 4 * (4 + 2 + (10 if self.with_landm else 0))
         self.last_d2h = self.B * (self.keep_cap * (60 + 4) + 4)
 
-    def submit(self, loc, conf, landm, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000, nms_thres=0.4):
-        """``loc``/``conf``/``landm``: contiguous CPU f32 tensors (pinned for the copies to overlap).  Returns the slot id."""
+    def submit(self, loc, conf, landm, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000, nms_thres=0.4,
+               cluster=0):
+        """``loc``/``conf``/``landm``: contiguous CPU f32 tensors (pinned for the copies to overlap).  Returns the slot id.
+        The call is asynchronous: the copies -- and, for pinned ``loc`` / ``landm``, the kernel itself, which reads candidate
+        and kept rows in place from host memory -- run after ``submit`` returns, so the three input buffers must stay
+        unmodified until ``wait(slot)``."""
         for t, shp in ((loc, (self.B, self.P, 4)), (conf, (self.B, self.P, 2))):
             if t.is_cuda or not t.is_contiguous() or tuple(t.shape) != shp or t.dtype != torch.float32:
                 raise ValueError("HostDetect expects contiguous CPU f32 tensors loc [B,P,4], conf [B,P,2], landm [B,P,10]")
@@ -387,7 +421,7 @@ class HostDetect(object):
         with torch.cuda.device(self.dev):
             _lib.call("jabd_detect_host_async", ptr(loc), ptr(conf), ptr(landm if self.with_landm else None), ptr(self.pri),
                       self.B, self.P, v0, v1, float(conf_thres), THRESH_GT if strict else THRESH_GE,
-                      int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), self.keep_cap, ptr(sl["dets"]),
+                      int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), self.keep_cap, int(cluster), ptr(sl["dets"]),
                       ptr(sl["counts"]), ptr(sl["keep_idx"]), ptr(sl["scratch"]), sl["scratch"].numel(),
                       ctypes.c_void_p(sl["stream"].cuda_stream))
             sl["done"].record(sl["stream"])

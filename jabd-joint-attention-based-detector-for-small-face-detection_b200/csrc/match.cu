@@ -679,6 +679,24 @@ size_t jabd_assign_host_scratch_bytes(int B, int64_t P, int64_t sumG, int with_l
     return n;
 }
 
+// Layout of the three target tensors inside the device staging area of jabd_assign_host (and of a host block that wants them
+// back in one copy): loc_t | conf_t | landm_t, each rounded up to 256 bytes.
+static void host_out_offsets(int B, int64_t P, int with_landm, size_t out[4])
+{
+    const size_t bp = (size_t)(B > 0 ? B : 0) * (size_t)(P > 0 ? P : 0);
+    out[0] = 0;
+    out[1] = round_up(sizeof(float) * 4 * bp, 256);
+    out[2] = out[1] + round_up(sizeof(int64_t) * bp, 256);
+    out[3] = out[2] + (with_landm ? round_up(sizeof(float) * 10 * bp, 256) : 0);
+}
+
+int jabd_assign_host_out_offsets(int B, int64_t P, int with_landm, size_t *offsets4)
+{
+    JABD_REQUIRE(B >= 0 && P >= 0 && offsets4, JABD_EINVAL, "assign_host_out_offsets: negative size or null pointer");
+    host_out_offsets(B, P, with_landm, offsets4);
+    return JABD_OK;
+}
+
 int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, const int *gt_off_host, int B, float threshold,
                      float var0, float var1, int label_mode, int encode_mode, int flags, float *loc_t_host,
                      int64_t *conf_t_host, float *landm_t_host, void *dev_scratch, size_t dev_scratch_bytes,
@@ -720,10 +738,22 @@ int jabd_assign_host(const float *priors_dev, int64_t P, const float *gt_host, c
                          d_conf, d_landm, nullptr, nullptr, nullptr, nullptr, d_ws, ws_bytes, stream);
     if (rc != JABD_OK) return rc;
     if (!dev_out) {
-        JABD_CUDA(cudaMemcpyAsync(loc_t_host, d_loc, sizeof(float) * 4 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
-        JABD_CUDA(cudaMemcpyAsync(conf_t_host, d_conf, sizeof(int64_t) * (size_t)B * P, cudaMemcpyDeviceToHost, st));
-        if (with_landm)
-            JABD_CUDA(cudaMemcpyAsync(landm_t_host, d_landm, sizeof(float) * 10 * (size_t)B * P, cudaMemcpyDeviceToHost, st));
+        // Host outputs laid out like the staging area (jabd_assign_host_out_offsets: one block, three views) come back
+        // in ONE copy; three unrelated buffers take three.
+        size_t o[4];
+        host_out_offsets(B, P, with_landm, o);
+        const char *h0 = reinterpret_cast<const char *>(loc_t_host);
+        const bool one_block = reinterpret_cast<const char *>(conf_t_host) == h0 + o[1] &&
+                               (!with_landm || reinterpret_cast<const char *>(landm_t_host) == h0 + o[2]);
+        const size_t bp = (size_t)B * (size_t)P;
+        if (one_block) {
+            const size_t bytes = with_landm ? o[2] + sizeof(float) * 10 * bp : o[1] + sizeof(int64_t) * bp;
+            JABD_CUDA(cudaMemcpyAsync(loc_t_host, d_loc, bytes, cudaMemcpyDeviceToHost, st));
+        } else {
+            JABD_CUDA(cudaMemcpyAsync(loc_t_host, d_loc, sizeof(float) * 4 * bp, cudaMemcpyDeviceToHost, st));
+            JABD_CUDA(cudaMemcpyAsync(conf_t_host, d_conf, sizeof(int64_t) * bp, cudaMemcpyDeviceToHost, st));
+            if (with_landm) JABD_CUDA(cudaMemcpyAsync(landm_t_host, d_landm, sizeof(float) * 10 * bp, cudaMemcpyDeviceToHost, st));
+        }
     }
     if (!(flags & JABD_ASSIGN_ASYNC)) JABD_CUDA(cudaStreamSynchronize(st));
     return JABD_OK;

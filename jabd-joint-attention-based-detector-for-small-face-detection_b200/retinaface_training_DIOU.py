@@ -62,12 +62,19 @@ class IouLoss(torch.nn.Module):
         dev = loc_p.device
         kind = LOC_LOSS.get(self.loss, _ops.CIOU)
         kind = kind if kind else _ops.CIOU
+        lp = loc_p.reshape(-1, 4)
+        n = int(lp.shape[0])
         lt = _tensor.to_dev(loc_t, dev).reshape(-1, 4)
         pri, v0, v1 = None, 0.0, 0.0
         if self.pred_mode == 'Center':
             pri = _tensor.to_dev(prior_data, dev).reshape(-1, 4)
             v0, v1 = _tensor.variances_of(self.variances)
-        return _IouLossFn.apply(loc_p.reshape(-1, 4), lt, pri, v0, v1, kind, bool(self.size_sum))
+        # the kernels index loc_t[i] and priors[i] for i < n: a row-count mismatch is the reference's broadcast error
+        # (decode(loc_p, prior_data) :338 / torch.min(bboxes1, bboxes2) :354), not a device out-of-bounds read
+        if int(lt.shape[0]) != n or (pri is not None and int(pri.shape[0]) != n):
+            raise ValueError("IouLoss: loc_p has %d rows, loc_t %d%s -- they must agree" % (
+                n, int(lt.shape[0]), "" if pri is None else ", prior_data %d" % int(pri.shape[0])))
+        return _IouLossFn.apply(lp, lt, pri, v0, v1, kind, bool(self.size_sum))
 
 
 class MultiBoxLoss(torch.nn.Module):

@@ -33,10 +33,9 @@ for (size, B, gen) in ((640, 32, "B"), (640, 1, "B"), (1024, 16, "B"), (1024, 16
     ws = _tensor.workspace(L.jabd_nms_workspace_bytes(B, P, keep_cap), dev)
     res = {}
     for mode, width in ((0, 1), (0, 2), (0, 0), (256, 0)):      # CTAs per image: 1, automatic
-        _lib.call("jabd_debug_set_detect_cluster", width)
 
         def run():
-            _lib.call("jabd_nms", ptr(bx), P * 4, 4, ptr(sc), P, 1, B, P, 0.02, 2, 5000, 0.4, mode, keep_cap, ptr(keep), ptr(cnt),
+            _lib.call("jabd_nms", ptr(bx), P * 4, 4, ptr(sc), P, 1, B, P, 0.02, 2, 5000, 0.4, mode | (width << 12), keep_cap, ptr(keep), ptr(cnt),
                       ptr(ws), ws.numel(), _tensor.stream_of(dev))
         for _ in range(3):
             run()

@@ -26,6 +26,18 @@ def header_symbols():
     return sorted(set(re.findall(r"JABD_API[^;(]*?\b(jabd_\w+)\s*\(", text)))
 
 
+def test_selftest_library_is_separate(lib):
+    """Test / bench hooks live in their own library and header; the product ABI does not export them."""
+    text = open(os.path.join(ROOT, "include", "jabd_b200_selftest.h")).read()
+    declared = sorted(set(re.findall(r"JABD_API[^;(]*?\b(jabd_\w+)\s*\(", text)))
+    assert declared == sorted(lib.SELFTEST_SIGNATURES)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib.SELFTEST_SO_PATH]).decode()
+    assert sorted(set(re.findall(r" T (jabd_\w+)", out))) == declared
+    lib.selftest_lib()
+    prod = subprocess.check_output(["nm", "-D", "--defined-only", lib.SO_PATH]).decode()
+    assert "selftest" not in prod and "debug" not in prod and "probe" not in prod
+
+
 def test_library_exports_every_declared_symbol(lib):
     declared = header_symbols()
     assert len(declared) >= 25
@@ -79,9 +91,15 @@ def test_host_side_validation_without_gpu(lib):
     mis = vp(buf.ctypes.data + 4)
     assert L.jabd_decode(mis, mis, 4, 1, 0.1, 0.2, mis, None) == -2
     assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 7, 0, 0.3, 0, 4, mis, mis, None, 0, None) == -1
-    # CTAs per image of the detect / NMS kernels: 0 (automatic), 1, 2, 4, 8 -- a host-side setting, no device call
-    assert L.jabd_debug_set_detect_cluster(3) == -1 and "CTAs per image" in lib.last_error()
-    assert L.jabd_debug_set_detect_cluster(2) == 0 and L.jabd_debug_set_detect_cluster(0) == 0
+    # CTAs per image of the detect / NMS kernels: a per-call option (0 automatic, 1, 2, 4, 8), validated before any device call
+    assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 0, 0, 0.3, 3 << 12, 4, mis, mis, None, 0, None) == -1
+    assert "CTAs per segment" in lib.last_error()
+    assert L.jabd_detect(None, None, None, None, 1, 4, 0.1, 0.2, 0.02, 2, 0, 0.4, 4, 3, None, None, None, None, 0, None) == -1
+    assert "CTAs per image" in lib.last_error()
+    assert L.jabd_nms_stats_offset(2, 750) == 24064 + 6144 and L.jabd_nms_workspace_bytes(2, 100, 750) == 24064 + 6144 + 256
+    offs = (ctypes.c_size_t * 4)()
+    assert L.jabd_assign_host_out_offsets(32, 16800, 1, offs) == 0
+    assert list(offs) == [0, 32 * 16800 * 16, 32 * 16800 * 24, 32 * 16800 * 64]
     # host-only GT packing helper (list of per-image arrays -> packed rows + offsets)
     import torch
     ts = [torch.rand(3, 15), torch.zeros(0, 15), torch.rand(5, 15)]

@@ -341,6 +341,6 @@ def test_shared_reciprocal_division_is_ieee(mods):
     out = torch.zeros(2, dtype=torch.int64, device="cuda")
     bad = torch.zeros(4, dtype=torch.float32, device="cuda")
     for seed in (1, 0x9E3779B97F4A7C15):
-        _lib.call("jabd_selftest_div", 1 << 30, seed, out.data_ptr(), bad.data_ptr(), None)
+        _lib.selftest_call("jabd_selftest_div", 1 << 30, seed, out.data_ptr(), bad.data_ptr(), None)
         torch.cuda.synchronize()
         assert int(out[0].item()) == 0, "mismatch (a, d, got, expected) = %s" % (bad.cpu().tolist(),)
