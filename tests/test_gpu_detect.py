@@ -557,7 +557,8 @@ def test_dlpack_inputs(mods):
     """north_star: the box utilities take numpy or framework tensors via DLPack.  An object that exports ONLY
     __dlpack__ / __dlpack_device__ (no torch or numpy type) goes through the same kernels: CUDA-resident in place, host
     memory through an explicit staging copy."""
-    ub, rt = mods["ub"], mods["rt"]
+    from jabd_b200 import retinaface_training as rt
+    ub = mods["ub"]
 
     class Capsule(object):
         def __init__(self, t):
