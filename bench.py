@@ -5,12 +5,12 @@
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (torch port)
 
 A *step* is one pass of target assignment (prior x GT IoU, both argmaxes, force-match, SSD encode) over one
-batch of BASELINE.json configs[1]: 32 images at 640x640 (16,800 priors), 1..300 synthetic faces per image.
-Per-GPU work is fixed (weak scaling): N ranks process N*32 images per step with no collective on the path.
+batch of BASELINE.json configs[1]: 32 images per GPU at 640x640 (16,800 priors), 1..300 synthetic faces per image.
+Weak scaling: N ranks process N*32 DISTINCT images per step, drawn from one pool of 256 images (= the cfg5 batch) at
+every N, cut into shards of equal estimated cost (LPT bin packing over images) -- no collective on the path.
 One JSON line is printed by rank 0.
 """
 import argparse
-import numpy as np
 import json
 import os
 import statistics
@@ -18,6 +18,8 @@ import subprocess
 import sys
 import tempfile
 import time
+
+import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -28,6 +30,7 @@ THR = 0.35
 IMAGE = (640, 640)
 BATCH = 32            # images per GPU per step (cfg2; cfg5 = 256 over 8 GPUs)
 SETS = 8              # rotating buffer sets: 8 x ~45 MB of outputs+workspace > 126 MB L2
+POOL = 256            # distinct images every N draws its global batches from (N = 8: one step = the whole pool = cfg5)
 METRIC = "images/s for prior match+encode and decode+NMS @640^2 (16.8k priors), 1-8 GPU"
 
 
@@ -38,6 +41,10 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -99,6 +106,20 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ reference
+def cpu_assign_rate(tp, torch, targets, pri, threads, budget_s, max_reps=200):
+    """images/s of oracle/torch_port.assign_batch on `threads` host threads over repeated passes of `targets` (~budget_s)."""
+    torch.set_num_threads(threads)
+    tp.assign_batch(THR, targets[:1], pri, list(VAR))
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        tp.assign_batch(THR, targets, pri, list(VAR))
+        reps += 1
+        if time.perf_counter() - t0 > budget_s or reps >= max_reps:
+            break
+    return len(targets) * reps / (time.perf_counter() - t0), reps
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path: the per-image loop of MultiBoxLoss.forward
     (R/nets/retinaface_training.py:197-214) restated op for op in torch (oracle/torch_port.py; the reference is
@@ -110,7 +131,7 @@ def run_reference(args):
     from jabd_b200 import config, synth
     from oracle import oracle as orc
     from oracle import torch_port as tp
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = host_cores()
     torch.set_num_threads(cores)
     pri = torch.from_numpy(orc.priors(config.cfg_mnet, IMAGE))
     targets = synth.make_gt_batch(2, BATCH, IMAGE)
@@ -127,6 +148,7 @@ def run_reference(args):
         tp.assign_batch(THR, sample, pri, list(VAR))
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
+    one_thread, reps1 = cpu_assign_rate(tp, torch, targets[:4], pri, 1, 4.0)
     desc = "first %d of the %d images of the cfg2 batch per step, torch %s CPU, %d threads" % (per_step, BATCH, torch.__version__, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -135,7 +157,10 @@ def run_reference(args):
         "config": {"workload": "cfg2 training target assignment (match+encode): 640x640, 16800 priors, 1..300 GT/image; "
                                "CPU sample of %d images per step" % per_step, "global_batch": per_step, "image": list(IMAGE),
                    "priors": int(pri.shape[0])},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc,
+                         "one_thread": {"value": one_thread, "unit": "images/s", "cores": 1,
+                                        "sample": "%d x the first 4 images, torch.set_num_threads(1)" % reps1},
+                         "os_cpu_count": os.cpu_count(), "sched_getaffinity": cores},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -156,6 +181,23 @@ def emit(line):
 _REAL_STDOUT = None
 
 
+def bind_cpus(local, local_world):
+    """One disjoint slice of the host's vCPUs per rank (eight ranks submitting a graph launch every ~40 us and driving PCIe
+    copies otherwise share -- and migrate across -- the same cores).  Returns (cpus of this rank, cpus visible before)."""
+    if not hasattr(os, "sched_getaffinity"):
+        return None, None
+    cpus = sorted(os.sched_getaffinity(0))
+    per = len(cpus) // max(local_world, 1)
+    if local_world > 1 and per >= 1:
+        mine = cpus[local * per:(local + 1) * per]
+        try:
+            os.sched_setaffinity(0, mine)
+            return mine, cpus
+        except Exception:
+            pass
+    return cpus, cpus
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -167,20 +209,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the detect / dense / phase side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the detect / dense / loss / cfg1 / cfg4 / cfg5 side measurements")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind each rank to its own slice of the host's vCPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
-    import ctypes
-    import torch
-    import torch.distributed as dist
-    from jabd_b200 import _lib, _tensor, anchors, batched, config, synth
-    from jabd_b200._tensor import ptr
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    my_cpus, all_cpus = (None, None) if args.no_affinity else bind_cpus(local, local_world)   # before torch spawns its threads
+
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from jabd_b200 import _lib, _tensor, anchors, batched, config, sharding, synth
+    from jabd_b200._tensor import ptr
+
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU path"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -190,7 +236,9 @@ def main():
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     L = _lib.lib()
-    stream = torch.cuda.current_stream(dev)
+
+    def cur_stream():
+        return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
     def barrier():
         if world > 1:
@@ -204,56 +252,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- workload: SETS distinct batches, all resident in HBM before timing
-    pri = anchors.Anchors(config.cfg_mnet, image_size=IMAGE).get_anchors()
-    P = int(pri.shape[0])
-    sets = []
-    from jabd_b200 import sharding
-    for s in range(SETS):
-        # step s%SETS processes a global batch of world*BATCH images; every rank generates the (cheap, seeded) GT of the
-        # whole batch and keeps its contiguous shard, cut by estimated cost, not image count (sharding.local_targets)
-        # weak scaling compares identical per-GPU work: the global batch of step s is the N=1 batch of step s once per rank
-        # (world * BATCH images), cut into contiguous shards of equal estimated cost by the same code a real run uses
-        tg_all = synth.make_gt_batch(2, BATCH, IMAGE, first_image=s * BATCH) * world
-        tg, (lo, hi) = sharding.local_targets(tg_all, rank, world, balance=True)
-        nb = len(tg)
-        gt, offs, offs_host = batched.pack_targets([t for t in tg], dev)
-        sumG = int(gt.shape[0])
-        ws = _tensor.workspace(L.jabd_assign_workspace_bytes(nb, P, sumG), dev)
-        sets.append(dict(host=tg, gt=gt, offs=offs, sumG=sumG, ws=ws, B=nb,
-                         loc=torch.empty((nb, P, 4), dtype=torch.float32, device=dev),
-                         conf=torch.empty((nb, P), dtype=torch.int64, device=dev),
-                         landm=torch.empty((nb, P, 10), dtype=torch.float32, device=dev)))
-    mean_g = sum(s["sumG"] for s in sets) / float(sum(s["B"] for s in sets))
-
-    def assign(s, flags=0, st=None):
-        _lib.call("jabd_assign", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], THR, VAR[0], VAR[1], 0, 1, flags,
-                  ptr(s["loc"]), ptr(s["conf"]), ptr(s["landm"]), None, None, None, None, ptr(s["ws"]), s["ws"].numel(),
-                  ctypes.c_void_p((st or torch.cuda.current_stream(dev)).cuda_stream))
-
-    def phase_match(s, flags=0):
-        _lib.call("jabd_assign_match", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], flags, ptr(s["ws"]),
-                  s["ws"].numel(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-
-    def phase_encode(s):
-        _lib.call("jabd_assign_encode", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], THR, VAR[0], VAR[1], 0, 1,
-                  ptr(s["loc"]), ptr(s["conf"]), ptr(s["landm"]), None, None, None, None, ptr(s["ws"]), s["ws"].numel(),
-                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-
-    # one CUDA graph per buffer set: the step is 3 kernel launches, replayed from a single graph launch
-    for s in sets:
-        assign(s)
-    torch.cuda.synchronize(dev)
-    graphs = []
-    for s in sets:
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            assign(s)
-        graphs.append(g)
+    def per_rank(x):
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = torch.empty((world,), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.tolist()]
 
     last_rank_ms = [None]
 
     def timed_loop(fn, n):
+        """n calls of fn(k) between two events on the current stream, a barrier + device sync on both sides; returns the
+        slowest rank's milliseconds (this rank's own in last_rank_ms) and the wall-clock window."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.time()
@@ -265,28 +276,130 @@ def main():
         last_rank_ms[0] = e0.elapsed_time(e1)
         return max_over_ranks(last_rank_ms[0]), (t0, time.time())
 
-    def per_rank(x):
-        if world == 1:
-            return [x]
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        out = torch.empty((world,), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(out, t)
-        return [float(v) for v in out.tolist()]
+    # ---- workload: every N draws its global batches (N*32 images per step) from the same pool of 256 distinct images, so
+    # the per-image GT statistics -- hence the work per image -- are identical at every N; set s of a rank is its LPT shard
+    # (equal estimated cost, sharding.lpt_shards) of global batch s.  N = 1: the shard is the whole batch (the cfg2 batches
+    # s*32 .. s*32+31); N = 8: every step is the whole pool = BASELINE configs[4], 256 distinct images over 8 ranks.
+    pri = anchors.Anchors(config.cfg_mnet, image_size=IMAGE).get_anchors()
+    P = int(pri.shape[0])
+    pool = synth.make_gt_batch(2, POOL, IMAGE)
+    costs = sharding.image_costs(pool)
+
+    def global_batch(s):
+        return [(s * world * BATCH + j) % POOL for j in range(world * BATCH)]
+
+    def shard_of(s, r):
+        g = global_batch(s)
+        return [g[i] for i in sharding.lpt_shards([costs[i] for i in g], world)[r]]
+
+    def make_set(images):
+        tg = [pool[i] for i in images]
+        gt, offs, _ = batched.pack_targets(tg, dev)
+        nb, sumG = len(tg), int(gt.shape[0])
+        return dict(images=images, host=tg, gt=gt, offs=offs, sumG=sumG, B=nb,
+                    ws=_tensor.workspace(L.jabd_assign_workspace_bytes(nb, P, sumG), dev),
+                    loc=torch.empty((nb, P, 4), dtype=torch.float32, device=dev),
+                    conf=torch.empty((nb, P), dtype=torch.int64, device=dev),
+                    landm=torch.empty((nb, P, 10), dtype=torch.float32, device=dev))
+
+    sets = [make_set(shard_of(s, rank)) for s in range(SETS)]
+    mean_g = sum(s["sumG"] for s in sets) / float(sum(s["B"] for s in sets))
+
+    def assign(s, flags=0):
+        _lib.call("jabd_assign", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], THR, VAR[0], VAR[1], 0, 1, flags,
+                  ptr(s["loc"]), ptr(s["conf"]), ptr(s["landm"]), None, None, None, None, ptr(s["ws"]), s["ws"].numel(), cur_stream())
+
+    def phase_match(s, flags=0):
+        _lib.call("jabd_assign_match", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], flags, ptr(s["ws"]),
+                  s["ws"].numel(), cur_stream())
+
+    def phase_encode(s):
+        _lib.call("jabd_assign_encode", ptr(pri), P, ptr(s["gt"]), ptr(s["offs"]), s["B"], s["sumG"], THR, VAR[0], VAR[1], 0, 1,
+                  ptr(s["loc"]), ptr(s["conf"]), ptr(s["landm"]), None, None, None, None, ptr(s["ws"]), s["ws"].numel(), cur_stream())
+
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def step_graphs(ss):
+        """One graph per buffer set (a step = 3 kernel launches) and one graph holding a step of every set back to back: the
+        timed loop replays the long one while >= SETS steps remain, so that the host's launch cadence (one cudaGraphLaunch
+        per ~40 us step, from N processes on shared vCPUs) is not what is measured."""
+        for s_ in ss:
+            assign(s_)
+        torch.cuda.synchronize(dev)
+        singles = [capture(lambda s_=s_: assign(s_)) for s_ in ss]
+        chunk = capture(lambda: [assign(s_) for s_ in ss])
+        return singles, chunk
+
+    singles, chunk = step_graphs(sets)
+
+    def run_steps(n, singles=singles, chunk=chunk):
+        k = 0
+        while n - k >= SETS:
+            chunk.replay()
+            k += SETS
+        while k < n:
+            singles[k % SETS].replay()
+            k += 1
 
     sampler = ClockSampler(local) if rank == 0 else None
     windows = []
-    for k in range(W):
-        graphs[k % SETS].replay()
-    ms, win = timed_loop(lambda k: graphs[k % SETS].replay(), K)
+    run_steps(W)
+    ms, win = timed_loop(lambda k: run_steps(K) if k == 0 else None, 1)
     windows.append(win)
     rank_ms = per_rank(last_rank_ms[0])                     # every rank's own device time for the K steps
     rank_images = per_rank(float(sum(s_["B"] for s_ in sets)) / SETS)
     rank_gt = per_rank(float(sum(s_["sumG"] for s_ in sets)) / SETS)
+    rank_cost = per_rank(float(sum(costs[i] for s_ in sets for i in s_["images"])) / SETS)
     value = world * BATCH * K / (ms / 1e3)
     # hold the same load for ~1.5 s so that the 50 ms clock sampler sees the GPU under this workload
-    hold = max(int(1.5e3 / max(ms / K, 1e-3)), 1)
-    _, win = timed_loop(lambda k: graphs[k % SETS].replay(), hold)
+    hold = max(int(1.5e3 / max(ms / K, 1e-3)), SETS)
+    _, win = timed_loop(lambda k: run_steps(hold) if k == 0 else None, 1)
     windows.append(win)
+
+    # ---- N > 1: (a) what a rank computed for its shard is what one GPU computes for the same images (per-image signature:
+    # positives, label sum, bit-pattern sums of loc_t and landm_t), checked on rank 0 for every image of global batch 0;
+    # (b) scaling control: the N = 1 batch replicated on every rank (identical work), to separate imbalance from the rest.
+    def signature(loc, conf, landm):
+        return torch.stack([(conf != 0).sum(1), conf.sum(1), loc.view(torch.int32).long().sum((1, 2)),
+                            landm.view(torch.int32).long().sum((1, 2))], 1).cpu()
+
+    shard_check, control = None, None
+    if world > 1:
+        assign(sets[0])
+        mine = (sets[0]["images"], signature(sets[0]["loc"], sets[0]["conf"], sets[0]["landm"]).tolist())
+        got = [None] * world
+        dist.all_gather_object(got, mine)
+        if rank == 0:
+            g0 = global_batch(0)
+            full = make_set(g0)
+            assign(full)
+            want = {img: row for img, row in zip(g0, signature(full["loc"], full["conf"], full["landm"]).tolist())}
+            seen, bad = [], []
+            for r, (imgs, rows) in enumerate(got):
+                for img, row in zip(imgs, rows):
+                    seen.append(img)
+                    if want[img] != row:
+                        bad.append((r, img))
+            covered = sorted(seen) == sorted(g0)
+            shard_check = {"images": len(g0), "equal": not bad and covered, "covered_once": covered, "mismatches": bad[:8],
+                           "what": "per-image (positives, sum conf_t, bit sums of loc_t and landm_t) of every rank's LPT shard of global "
+                                   "batch 0 == the same images assigned on rank 0's GPU alone",
+                           "positives_total": int(sum(row[0] for row in want.values()))}
+            del full
+            assert shard_check["equal"], "sharded result differs from the single-GPU result: %s" % (shard_check,)
+        ctrl_sets = [make_set(list(range(s * BATCH, (s + 1) * BATCH))) for s in range(SETS)]
+        c_singles, c_chunk = step_graphs(ctrl_sets)
+        run_steps(W, c_singles, c_chunk)
+        ms_c, _ = timed_loop(lambda k: run_steps(K, c_singles, c_chunk) if k == 0 else None, 1)
+        control = {"value": world * BATCH * K / (ms_c / 1e3), "unit": "images/s", "ms_per_step": ms_c / K,
+                   "per_rank_ms_per_step": [x / K for x in per_rank(last_rank_ms[0])],
+                   "what": "identical work on every rank: the N = 1 batches (images s*32..s*32+31) once per rank -- round 1's weak-"
+                           "scaling workload, kept as the control that separates shard imbalance from everything else"}
+        del ctrl_sets, c_singles, c_chunk
 
     # ---- per-kernel phases (CUDA events on the launching stream, same rotating buffers)
     # One CUDA graph per phase holding that phase for all SETS buffer sets back to back, so that the host's launch
@@ -297,11 +410,7 @@ def main():
         for s_ in sets:
             fn(s_)
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for s_ in sets:
-                fn(s_)
-        return g
+        return capture(lambda: [fn(s_) for s_ in sets])
 
     g_prep = phase_graph(lambda s_: phase_match(s_, 2))        # JABD_ASSIGN_PREP_ONLY
     g_pm = phase_graph(lambda s_: phase_match(s_))             # prep + match
@@ -317,18 +426,21 @@ def main():
     sum_g = sum(s["sumG"] for s in sets) / SETS
     pairs = float(P) * sum_g                                   # prior x GT pairs per launch
     flops_launch = 14.0 * pairs                                # 14 fp32 ops per pair, no FMA
-    mean_b = sum(s["B"] for s in sets) / float(SETS)          # == BATCH on one GPU; GT-balanced shards vary by a few images
+    mean_b = sum(s["B"] for s in sets) / float(SETS)          # == BATCH on one GPU; cost-balanced shards vary by a few images
     bytes_step = mean_b * (80.0 * P) + 60.0 * sum_g            # 80P + 60G per image
 
     # measured FP32 (non-FMA) peak: dependency-free FMUL/FADD chains on every SM, same clocks as the run
+    # (libjabd_b200_selftest.so: a bench hook, not part of the product ABI)
     sms = ctypes.c_int(0)
     _lib.call("jabd_device_info", ctypes.byref(sms), None, None)
     sink = torch.zeros(4, dtype=torch.float32, device=dev)
     probe_ctas, probe_iters = sms.value * 16, 4096
+
+    def probe(k=0):
+        _lib.selftest_call("jabd_selftest_fp32_probe", probe_ctas, probe_iters, ptr(sink), cur_stream())
     for _ in range(3):
-        _lib.call("jabd_fp32_probe", probe_ctas, probe_iters, ptr(sink), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-    ms_probe, _ = timed_loop(lambda k: _lib.call("jabd_fp32_probe", probe_ctas, probe_iters, ptr(sink),
-                                                 ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), 20)
+        probe()
+    ms_probe, _ = timed_loop(probe, 20)
     fp32_peak = probe_ctas * 256 * 32.0 * probe_iters / (ms_probe / 20 * 1e-3) / 1e12      # Tops/s
     fp32_nominal = sms.value * 128 * 1.965e9 / 1e12
 
@@ -340,15 +452,19 @@ def main():
         pass
     match_tflops = flops_launch / (us_match * 1e-6) / 1e12
     enc_gbs = bytes_step / (us_enc * 1e-6) / 1e9
+    t_fp32_us = flops_launch / (fp32_peak * 1e12) * 1e6
+    t_hbm_us = bytes_step / (hbm_peak * 1e9) * 1e6
     # dominant kernel of the step = assign_match_kernel (FP32-pipe bound: no contraction, ~0.3 MB of DRAM reads)
     roofline = {"kernel": "assign_match_kernel", "bound": "fp32", "achieved": match_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": match_tflops / fp32_peak, "traffic": traffic.get("assign_match_kernel_bytes_per_launch"),
-                "peak_source": "measured in this run: jabd_fp32_probe (FMUL+FADD chains, no FMA) on %d SMs; nominal %d x 128 lanes x "
-                               "1.965 GHz = %.1f" % (sms.value, sms.value, fp32_nominal),
+                "peak_source": "measured in this run: jabd_selftest_fp32_probe (FMUL+FADD chains, no FMA) on %d SMs; nominal %d x 128 "
+                               "lanes x 1.965 GHz = %.1f" % (sms.value, sms.value, fp32_nominal),
                 "algorithmic_flops_per_launch": flops_launch, "launch_us": us_match,
                 "launch_us_how": "CUDA events around graphs of %d launches: (prep+match) - (prep alone), %d replays each" % (SETS, n_ph),
                 "note": "achieved = 14 fp32 ops x P x sum(G) (dense-equivalent, SURVEY 8d) / kernel time; the kernel culls GT "
-                        "against each warp's prior bounding box, so executed flops are lower than this (see phases.match_dense_*)"}
+                        "against each warp's prior bounding box, so executed flops are lower than this (see phases.match_dense_*)",
+                "step": {"ms_per_step": ms / K, "bound_us": max(t_fp32_us, t_hbm_us), "frac": max(t_fp32_us, t_hbm_us) / (ms / K * 1e3),
+                         "note": "whole step (all launches) against max(t_FP32 dense-equivalent, t_HBM) of SURVEY 8(d)"}}
     roofline_encode = {"kernel": "match_encode_kernel", "bound": "hbm", "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s",
                        "frac": enc_gbs / hbm_peak, "traffic": traffic.get("match_encode_kernel_bytes_per_launch"),
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_step, "launch_us": us_enc,
@@ -356,8 +472,8 @@ def main():
     phases = {"prep_us": us_prep, "match_us": us_match, "match_encode_us": us_enc,
               "match_dense_equiv_tflops": match_tflops, "fp32_peak_measured_tops": fp32_peak, "fp32_peak_nominal_tops": fp32_nominal}
 
-    extras = {}
-    if not args.no_extras:
+    extras = not args.no_extras
+    if extras:
         # dense (no culling) matching: every one of the P*G pairs evaluated once -> executed-flops figure
         g_dense = phase_graph(lambda s_: phase_match(s_, 1))
         g_dense.replay()
@@ -370,8 +486,9 @@ def main():
 
     # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region
     # (fixed BATCH images per rank and step here: the transfer volume, which bounds this path, is set by B*P)
-    host_sets = [synth.make_gt_batch(2, BATCH, IMAGE, first_image=(rank * SETS + s_) * BATCH) for s_ in range(SETS)]
-    host = batched.HostAssign(pri, BATCH, max(sum(int(t.shape[0]) for t in hs) for hs in host_sets))
+    host_sets = [[pool[((rank * SETS + s_) * BATCH + j) % POOL] for j in range(BATCH)] for s_ in range(SETS)]
+    cap_g = max(sum(int(t.shape[0]) for t in hs) for hs in host_sets)
+    host = batched.HostAssign(pri, BATCH, cap_g)
     n_e2e = min(K, 100)
     for k in range(3):
         host(host_sets[k % SETS])
@@ -384,21 +501,13 @@ def main():
         if k == n_e2e - 1:                  # drain inside the timed region
             host.wait(pend.pop(0))
     ms_e2e, _ = timed_loop(e2e_step, n_e2e)
+    e2e_rank_ms = per_rank(last_rank_ms[0])
     e2e_value = world * BATCH * n_e2e / (ms_e2e / 1e3)
     ms_e2e_sync, _ = timed_loop(lambda k: host(host_sets[k % SETS]), n_e2e)   # same call, one batch at a time
     # variant: the training flow -- GT rows from pinned host memory in, targets left in HBM for the loss (what
     # MultiBoxLoss.forward does with them), the step's result read back = the per-image positive counts.  Same C-ABI call
     # with JABD_ASSIGN_DEVICE_OUT, two slots.
-    dsets = []
-    for hs in host_sets[:1]:
-        gt_d, offs_d, _ = batched.pack_targets(hs, dev)
-        sg = int(gt_d.shape[0])
-        dsets.append(dict(gt=gt_d, offs=offs_d, sumG=sg, B=BATCH,
-                          ws=_tensor.workspace(L.jabd_assign_workspace_bytes(BATCH, P, sg), dev),
-                          loc=torch.empty((BATCH, P, 4), dtype=torch.float32, device=dev),
-                          conf=torch.empty((BATCH, P), dtype=torch.int64, device=dev),
-                          landm=torch.empty((BATCH, P, 10), dtype=torch.float32, device=dev)))
-    host_dev = batched.HostAssign(pri, BATCH, max(sum(int(t.shape[0]) for t in hs) for hs in host_sets), device_out=True)
+    host_dev = batched.HostAssign(pri, BATCH, cap_g, device_out=True)
     cnt_pin = [torch.empty((BATCH,), dtype=torch.int64).pin_memory() for _ in range(2)]
     cnt_done = [torch.cuda.Event() for _ in range(2)]
     pend_dev = []
@@ -424,23 +533,47 @@ def main():
     while pend_dev:
         collect(0)
     ms_e2e_dev, _ = timed_loop(e2e_device_out, n_e2e)
-    e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host.last_h2d, "d2h_bytes_per_step": host.last_d2h,
+    d2h_step = host.last_d2h
+    e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": host.last_h2d, "d2h_bytes_per_step": d2h_step,
            "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
+           "per_rank": {"ms_per_step": [x / n_e2e for x in e2e_rank_ms],
+                        "d2h_GBps": [d2h_step / (x / n_e2e * 1e-3) / 1e9 for x in e2e_rank_ms],
+                        "aggregate_d2h_GBps": world * d2h_step / (ms_e2e / n_e2e * 1e-3) / 1e9,
+                        "note": "every rank moves the same bytes; this path is bound by the D2H copy of the targets (34.4 MB per "
+                                "rank and step over that rank's PCIe link into pinned host memory)"},
            "api": "batched.HostAssign.submit/wait -> jabd_assign_host (JABD_ASSIGN_ASYNC, 2 slots): list of per-image GT "
-                  "tensors packed into pinned memory and copied in, all three target tensors copied out to pinned host memory, "
-                  "every step; step k+1 is submitted before step k is collected",
+                  "tensors packed into pinned memory and copied in, all three target tensors copied out to pinned host memory "
+                  "(one block, one D2H copy), every step; step k+1 is submitted before step k is collected",
            "synchronous_call": {"value": world * BATCH * n_e2e / (ms_e2e_sync / 1e3), "unit": "images/s",
                                 "ms_per_step": ms_e2e_sync / n_e2e, "note": "HostAssign(targets): one batch at a time"},
            "device_resident_targets": {"value": world * BATCH * n_e2e / (ms_e2e_dev / 1e3), "unit": "images/s",
+                                       "ms_per_step": ms_e2e_dev / n_e2e,
                                        "h2d_bytes_per_step": host_dev.last_h2d, "d2h_bytes_per_step": BATCH * 8,
                                        "note": "batched.HostAssign(device_out=True) -> jabd_assign_host(JABD_ASSIGN_DEVICE_OUT | ASYNC), two "
                                                "slots: per-image GT tensors packed into pinned memory and copied in, targets stay in HBM "
-                                               "for the loss (what MultiBoxLoss.forward does with them), per-image positive counts read back"}}
+                                               "for the loss (what MultiBoxLoss.forward does with them, R/nets/retinaface_training.py:"
+                                               "223-227), per-image positive counts read back"}}
+    del host, host_dev
+
+    cpu_ok = rank == 0 and world == 1 and not args.no_cpu_baseline
+    cores = host_cores()
+    if cpu_ok:
+        from oracle import torch_port as tp
+
+    def cpu_rate(fn, items, budget_s, max_reps):
+        """items/s of a CPU port closure on all host threads, bounded."""
+        torch.set_num_threads(cores)
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < budget_s and reps < max_reps:
+            fn()
+            reps += 1
+        return items * reps / (time.perf_counter() - t0), reps
 
     # ---- SURVEY 8(f) rank 1: the whole MultiBoxLoss.forward + backward on the device (assign -> mining -> sums -> grads)
     loss_info = None
-    if not args.no_extras:
-        ds0 = dsets[0]
+    if extras:
+        ds0 = make_set(list(range(BATCH)))
         preds_l = [synth.make_logits(2, i, P) for i in range(BATCH)]
         pl, pc, pm = (torch.stack([q[j] for q in preds_l]).to(dev) for j in range(3))
         losses = torch.empty((3,), dtype=torch.float32, device=dev)
@@ -451,17 +584,14 @@ def main():
         gin = torch.ones((3,), dtype=torch.float32, device=dev)
 
         def loss_step():
-            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             assign(ds0)
             _lib.call("jabd_multibox_loss_forward", ptr(pl), ptr(pc), ptr(pm), ptr(ds0["loc"]), ptr(ds0["conf"]), ptr(ds0["landm"]),
-                      BATCH, P, 7, ptr(losses), ptr(norms), ptr(lmask), ptr(lws), lws.numel(), st)
+                      BATCH, P, 7, ptr(losses), ptr(norms), ptr(lmask), ptr(lws), lws.numel(), cur_stream())
             _lib.call("jabd_multibox_loss_backward", ptr(pl), ptr(pc), ptr(pm), ptr(ds0["loc"]), ptr(ds0["landm"]), ptr(lmask),
-                      ptr(norms), ptr(gin), BATCH, P, ptr(gl), ptr(gc), ptr(gm), st)
+                      ptr(norms), ptr(gin), BATCH, P, ptr(gl), ptr(gc), ptr(gm), cur_stream())
         loss_step()
         torch.cuda.synchronize(dev)
-        g_loss = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_loss):
-            loss_step()
+        g_loss = capture(loss_step)
         g_loss.replay()
         ms_loss, _ = timed_loop(lambda k: g_loss.replay(), 200)
         loss_info = {"images_per_s": world * BATCH * 200 / (ms_loss / 1e3), "us_per_batch": ms_loss / 200 * 1e3,
@@ -469,35 +599,36 @@ def main():
                      "what": "assign (3 launches) + hard-negative mining / loss sums (3) + gradients w.r.t. the predictions (1) "
                              "for 32 x 640^2 images, synthetic logits, everything resident in HBM; replaces "
                              "R/nets/retinaface_training.py:183-303 + autograd backward"}
-        if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            from oracle import torch_port as tp2
-            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        if cpu_ok:
             nb = 8
             cpu_preds = tuple(t[:nb].cpu().clone().requires_grad_(True) for t in (pl, pc, pm))
-            t0 = time.perf_counter()
-            reps = 0
-            while time.perf_counter() - t0 < 6.0 and reps < 10:
+
+            def cpu_loss():
                 for q in cpu_preds:
                     q.grad = None
-                a_, b_, c_ = tp2.multibox_loss(cpu_preds, pri.cpu(), host_sets[0][:nb], THR, list(VAR), 7)
+                a_, b_, c_ = tp.multibox_loss(cpu_preds, pri.cpu(), pool[:nb], THR, list(VAR), 7)
                 (a_ + b_ + c_).backward()
-                reps += 1
-            loss_info["cpu_port_images_per_s"] = nb * reps / (time.perf_counter() - t0)
+            r, reps = cpu_rate(cpu_loss, nb, 5.0, 10)
+            loss_info["cpu_port_images_per_s"] = r
             loss_info["cpu_port_sample"] = "%d x the first %d images, oracle/torch_port.multibox_loss forward+backward" % (reps, nb)
+        del ds0, pl, pc, pm, gl, gc, gm, lmask
+
+    def clustered_preds(cfg_id, size, pr, first, n, count=None):
+        locs, confs, lms = [], [], []
+        for i in range(first, first + n):
+            gti = synth.make_gt(cfg_id, i, size, count=count)
+            l, c, m = synth.make_preds_clustered(cfg_id, i, pr, gti, VAR, device=dev)
+            locs.append(l); confs.append(c); lms.append(m)
+        return torch.stack(locs).contiguous(), torch.stack(confs).contiguous(), torch.stack(lms).contiguous()
 
     # ---- inference side: decode+top-k+NMS at 640^2 (the metric's second half) and at cfg3's 1024^2
     detect_info = None
-    if not args.no_extras:
+    if extras:
         detect_info = {}
-        for name, size, B, cfg_id in (("640x640_b32", (640, 640), 32, 3), ("cfg3_1024x1024_b16", (1024, 1024), 16, 3)):
+        for name, size, B in (("640x640_b32", (640, 640), 32), ("cfg3_1024x1024_b16", (1024, 1024), 16)):
             pr = anchors.cached_priors(config.cfg_mnet, size, dev)
             Pd = int(pr.shape[0])
-            locs, confs, lms = [], [], []
-            for i in range(B):
-                gti = synth.make_gt(3, i, size, count=60)
-                l, c, m = synth.make_preds_clustered(3, i, pr, gti, VAR, device=dev)
-                locs.append(l); confs.append(c); lms.append(m)
-            loc_h, conf_h, lm_h = torch.stack(locs).contiguous(), torch.stack(confs).contiguous(), torch.stack(lms).contiguous()
+            loc_h, conf_h, lm_h = clustered_preds(3, size, pr, 0, B, count=60)
             loc_d, conf_d, lm_d = loc_h.to(dev), conf_h.to(dev), lm_h.to(dev)
             for _ in range(3):
                 out = batched.detect(loc_d, conf_d, lm_d, pr, VAR)
@@ -521,36 +652,25 @@ def main():
                                  "e2e_images_per_s": world * B * n_d / (ms_dh / 1e3), "e2e_h2d_bytes": hd.last_h2d,
                                  "e2e_d2h_bytes": hd.last_d2h, "priors": Pd, "batch": B, "mean_kept": float(out[1].float().mean()),
                                  "params": "score>0.02, top-5000, IoU 0.4, keep 750; clustered synthetic predictions"}
-            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            if cpu_ok:
                 # the reference's per-image post-processing on the host cores (decode, decode_landm, cat, threshold, top-k,
                 # torchvision NMS; R/predict.py:167-181 composed per SURVEY D4), bounded sample
-                from oracle import torch_port as tp3
-                torch.set_num_threads(len(os.sched_getaffinity(0)))
                 nb = min(B, 4)
                 pr_c = pr.cpu()
-                t0 = time.perf_counter()
-                reps = 0
-                while time.perf_counter() - t0 < 4.0 and reps < 5:
-                    for i in range(nb):
-                        tp3.infer_one_topk(loc_h[i], conf_h[i], lm_h[i], pr_c, list(VAR), 0.02, 5000, 0.4, 750)
-                    reps += 1
-                detect_info[name]["cpu_port_images_per_s"] = nb * reps / (time.perf_counter() - t0)
+                r, reps = cpu_rate(lambda: [tp.infer_one_topk(loc_h[i], conf_h[i], lm_h[i], pr_c, list(VAR), 0.02, 5000, 0.4, 750)
+                                            for i in range(nb)], nb, 4.0, 5)
+                detect_info[name]["cpu_port_images_per_s"] = r
                 detect_info[name]["cpu_port_sample"] = "%d x the first %d images, oracle/torch_port.infer_one_topk" % (reps, nb)
             # API-form decode (D1): HBM-bound elementwise kernel
-            outb = torch.empty_like(loc_d)
             big = [torch.randn((64, Pd, 4), device=dev) * 0.5 for _ in range(4)]
             outs = [torch.empty_like(b) for b in big]
 
             def dec(k):
-                _lib.call("jabd_decode", ptr(big[k % 4]), ptr(pr), Pd, 64, VAR[0], VAR[1], ptr(outs[k % 4]),
-                          ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                _lib.call("jabd_decode", ptr(big[k % 4]), ptr(pr), Pd, 64, VAR[0], VAR[1], ptr(outs[k % 4]), cur_stream())
             for k in range(4):
                 dec(k)
             torch.cuda.synchronize(dev)
-            g_dec = torch.cuda.CUDAGraph()              # 4 launches per replay: the host never limits a ~10 us kernel
-            with torch.cuda.graph(g_dec):
-                for k in range(4):
-                    dec(k)
+            g_dec = capture(lambda: [dec(k) for k in range(4)])  # 4 launches per replay: the host never limits a ~10 us kernel
             g_dec.replay()
             ms_dec, _ = timed_loop(lambda k: g_dec.replay(), 50)
             ms_dec /= 4.0
@@ -558,46 +678,133 @@ def main():
             detect_info[name]["decode_kernel"] = {"batch": 64, "GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
                                                   "bytes_per_launch": 64 * Pd * 32.0, "us": ms_dec / 50 * 1e3,
                                                   "l2": "4 rotating in/out sets of 64 images"}
-            del big, outs, outb
+            del big, outs, hd
+
+    # ---- BASELINE configs[0] and configs[3]: the reference's live shape (one image per call, R/predict.py:167-181) at 640^2
+    # with 50 faces, and the dense tiny-face stress (2048^2, 172,032 priors, 1,500 faces), one image per GPU.  Latency per call.
+    def one_image(cfg_id, size, image_idx, reps_assign, reps_detect):
+        pr = anchors.cached_priors(config.cfg_mnet, size, dev)
+        Pn = int(pr.shape[0])
+        gt1 = synth.make_gt(cfg_id, image_idx, size)
+        gtd, offs, _ = batched.pack_targets([gt1], dev)
+        G = int(gtd.shape[0])
+        ws = _tensor.workspace(L.jabd_assign_workspace_bytes(1, Pn, G), dev)
+        o = (torch.empty((1, Pn, 4), dtype=torch.float32, device=dev), torch.empty((1, Pn), dtype=torch.int64, device=dev),
+             torch.empty((1, Pn, 10), dtype=torch.float32, device=dev))
+
+        def call():
+            _lib.call("jabd_assign", ptr(pr), Pn, ptr(gtd), ptr(offs), 1, G, THR, VAR[0], VAR[1], 0, 1, 0, ptr(o[0]), ptr(o[1]),
+                      ptr(o[2]), None, None, None, None, ptr(ws), ws.numel(), cur_stream())
+        call()
+        torch.cuda.synchronize(dev)
+        g1 = capture(call)
+        g1.replay()
+        ms_a, _ = timed_loop(lambda k: g1.replay(), reps_assign)
+        for _ in range(2):
+            batched.assign_targets(pr, [gt1.to(dev)], threshold=THR, variances=VAR)
+        gt_dev = gt1.to(dev)
+        ms_api, _ = timed_loop(lambda k: batched.assign_targets(pr, [gt_dev], threshold=THR, variances=VAR), min(reps_assign, 50))
+        l1, c1, m1 = clustered_preds(cfg_id, size, pr, image_idx, 1)
+        l1, c1, m1 = l1.to(dev), c1.to(dev), m1.to(dev)
+        res = {"priors": Pn, "gt": G, "pairs": Pn * G,
+               "assign_us": ms_a / reps_assign * 1e3, "assign_images_per_s": world * reps_assign / (ms_a / 1e3),
+               "assign_api_us": ms_api / min(reps_assign, 50) * 1e3,
+               "assign_dense_equiv_frac_of_fp32": 14.0 * Pn * G / (ms_a / reps_assign * 1e-3) / 1e12 / fp32_peak,
+               "note": "assign_us: jabd_assign replayed from a CUDA graph (3 launches); assign_api_us: batched.assign_targets per call "
+                       "(allocation + ctypes + 3 launches, what a drop-in caller pays); one image per GPU"}
+        for tag, kw in (("detect_cfg3_params", dict()),
+                        ("detect_live_params", dict(conf_thres=0.5, strict=False, pre_nms_topk=0, nms_thres=0.3, keep_topk=0))):
+            for _ in range(2):
+                dd = batched.detect(l1, c1, m1, pr, VAR, **kw)
+            ms_d1, _ = timed_loop(lambda k: batched.detect(l1, c1, m1, pr, VAR, **kw), reps_detect)
+            res[tag + "_us"] = ms_d1 / reps_detect * 1e3
+            res[tag + "_kept"] = int(dd[1][0])
+        if cpu_ok:
+            pr_c, gtc = pr.cpu(), [gt1]
+            r, reps = cpu_rate(lambda: tp.assign_batch(THR, gtc, pr_c, list(VAR)), 1, 3.0, 50)
+            res["cpu_port_assign_images_per_s"] = r
+            lc, cc, mc = l1[0].cpu(), c1[0].cpu(), m1[0].cpu()
+            r, reps = cpu_rate(lambda: tp.infer_one_topk(lc, cc, mc, pr_c, list(VAR), 0.02, 5000, 0.4, 750), 1, 2.0, 20)
+            res["cpu_port_detect_cfg3_params_images_per_s"] = r
+            r, reps = cpu_rate(lambda: tp.infer_one(lc, cc, mc, pr_c, list(VAR), 0.5, 0.3), 1, 2.0, 20)
+            res["cpu_port_detect_live_params_images_per_s"] = r
+            res["cpu_port_cores"] = cores
+        return res
+
+    cfg1_info = cfg4_info = None
+    if extras:
+        cfg1_info = one_image(1, IMAGE, 0, 200, 50)
+        cfg1_info["what"] = "BASELINE configs[0]: batch 1, 640x640, 16,800 priors, 50 faces -- latency per call"
+        cfg4_info = one_image(4, (2048, 2048), rank, 50, 10)
+        cfg4_info["what"] = ("BASELINE configs[3]: 2048x2048, 172,032 priors, 1,500 faces, one image per GPU (image index = rank); "
+                             "live parameters = >= 0.5 / IoU 0.3 / nothing capped (R/predict.py:40,181)")
 
     # ---- cfg5 validation flow: detect the rank's shard, scale to pixels, all-gather the padded detections (the path's only
-    # collective, NCCL over NVLink), WIDER AP of the gathered set on rank 0 (SURVEY 8e + 8f ranks 2-3)
+    # collective, NCCL over NVLink, issued on a side stream behind an event so that it overlaps the NEXT batch's detection),
+    # WIDER AP of the gathered set on rank 0 (SURVEY 8e + 8f ranks 2-3)
     cfg5_info = None
-    if not args.no_extras:
+    if extras:
         from jabd_b200 import utils_map
-        size, B5 = (640, 640), 32
+        size, B5, keep5 = (640, 640), 32, 750
         pr5 = anchors.cached_priors(config.cfg_mnet, size, dev)
-        locs, confs, lms = [], [], []
-        for i in range(B5):
-            gi = rank * B5 + i
-            l, c, m = synth.make_preds_clustered(5, gi, pr5, synth.make_gt(5, gi, size, count=40), VAR, device=dev)
-            locs.append(l); confs.append(c); lms.append(m)
-        loc5, conf5, lm5 = (torch.stack(x).contiguous().to(dev) for x in (locs, confs, lms))   # resident in HBM
+        loc5, conf5, lm5 = (x.to(dev) for x in clustered_preds(5, size, pr5, rank * B5, B5, count=40))   # resident in HBM
         post5 = torch.from_numpy(batched.letterbox_params(size, [size] * B5)).to(dev)
+        gather = sharding.DetectionGather(B5, keep5, dev, depth=2)
+        kidx5 = torch.empty((B5, keep5), dtype=torch.int32, device=dev)
 
-        def cfg5_step():
-            d, c, _ = batched.detect(loc5, conf5, lm5, pr5, VAR)
+        def cfg5_step(k, overlap=True):
+            slot = k & 1
+            if k >= 2:
+                gather.result(slot)         # this slot's previous gather must have drained before its buffers are refilled
+            d, c = gather.dets(slot), gather.counts(slot)
+            batched.detect(loc5, conf5, lm5, pr5, VAR, keep_topk=keep5, out=(d, c, kidx5))
             batched.correct_boxes(d, c, post5, letterbox=False, to_pixels=True)
-            return sharding.allgather_detections(d, c)
-        for _ in range(3):
-            gd, gc = cfg5_step()
+            gather.launch(slot)
+            if not overlap:
+                gather.result(slot)         # serialised variant: the step's stream waits for its own gather
+        for k in range(4):
+            cfg5_step(k)
         n5 = 20
-        ms5, _ = timed_loop(lambda k: cfg5_step(), n5)
+
+        def cfg5_loop(overlap):
+            def body(k):
+                cfg5_step(k, overlap)
+                if k == n5 - 1:             # drain inside the timed region: the last gathers are part of the K steps
+                    gather.result((k - 1) & 1)
+                    gather.result(k & 1)
+            ms_, _ = timed_loop(body, n5)
+            return ms_
+        ms5 = cfg5_loop(True)
+        ms5_serial = cfg5_loop(False)
+        gd, gc = gather.result((n5 - 1) & 1)
+        torch.cuda.synchronize(dev)
+        # the collective alone, back to back
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d_loc, c_loc, _ = batched.detect(loc5, conf5, lm5, pr5, VAR)
         barrier()
         e0.record()
-        for _ in range(n5):
-            sharding.allgather_detections(d_loc, c_loc)
+        for k in range(n5):
+            gather.launch(k & 1)
+            gather.result(k & 1)
         e1.record()
         barrier()
         us_ag = max_over_ranks(e0.elapsed_time(e1)) / n5 * 1e3
-        cfg5_info = {"images_per_s": world * B5 * n5 / (ms5 / 1e3), "ms_per_step": ms5 / n5, "allgather_us": us_ag,
-                     "allgather_bytes_per_rank": int(d_loc.numel() * 4 + c_loc.numel() * 4),
-                     "what": "per rank: fused detect of 32 x 640^2 images (score>0.02, top-5000, IoU 0.4, keep 750) + pixel scaling, then "
-                             "one all_gather_into_tensor of dets [32,750,15] + counts over %s" % ("NCCL" if world > 1 else "a single rank (no-op)")}
+        ms_det_only, _ = timed_loop(lambda k: (batched.detect(loc5, conf5, lm5, pr5, VAR, keep_topk=keep5,
+                                                              out=(gather.dets(0), gather.counts(0), kidx5)),
+                                               batched.correct_boxes(gather.dets(0), gather.counts(0), post5, letterbox=False,
+                                                                     to_pixels=True)), n5)
+        cfg5_info = {"images_per_s": world * B5 * n5 / (ms5 / 1e3), "ms_per_step": ms5 / n5,
+                     "serialised_ms_per_step": ms5_serial / n5, "detect_only_ms_per_step": ms_det_only / n5,
+                     "allgather_us": us_ag, "allgather_overlapped": world > 1,
+                     "allgather_exposed_us": max(ms5 - ms_det_only, 0.0) / n5 * 1e3,
+                     "allgather_bytes_per_rank": int(gather.L * 4),
+                     "what": "per rank: fused detect of 32 x 640^2 images (score>0.02, top-5000, IoU 0.4, keep 750) + pixel scaling into "
+                             "the send buffer, then ONE all_gather_into_tensor of [32*750*15 floats | 32 counts] over %s on a side stream "
+                             "(sharding.DetectionGather, two slots): batch k+1 is detected while batch k is gathered; "
+                             "serialised_ms_per_step waits for each gather in line (round 1's flow)"
+                             % ("NCCL" if world > 1 else "a single rank (device copy)")}
         if rank == 0:
-            preds5 = utils_map.dets_to_pred_rows(gd, gc)
+            gd2 = gd.reshape(world * B5, keep5, 15).contiguous()
+            preds5 = utils_map.dets_to_pred_rows(gd2, gc.reshape(-1).contiguous())
             gts5, keeps5 = [], []
             for gi in range(world * B5):
                 t5 = synth.make_gt(5, gi, size, count=40)[:, :4].numpy().astype("float64") * size[0]
@@ -614,47 +821,53 @@ def main():
         sampler.stop()
         clocks = sampler.summary(windows)
 
-    # ---- CPU baseline (rank 0, single-GPU run only): torch port of the reference loop, bounded sample
+    # ---- CPU baseline (rank 0, single-GPU run only): torch port of the reference loop, bounded sample, all threads and one
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        from oracle import torch_port as tp
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        torch.set_num_threads(cores)
+    if cpu_ok:
         pri_c = pri.cpu()
-        sample = sets[0]["host"][:16]
-        tp.assign_batch(THR, sample[:2], pri_c, list(VAR))
-        t0 = time.perf_counter()
-        reps = 0
-        while True:
-            tp.assign_batch(THR, sample, pri_c, list(VAR))
-            reps += 1
-            if time.perf_counter() - t0 > 10.0 or reps >= 200:   # ~10 s of CPU work
-                break
-        dt = time.perf_counter() - t0
-        cpu = {"value": len(sample) * reps / dt, "unit": "images/s", "cores": cores, "kind": "port",
+        sample = pool[:16]
+        v_all, reps = cpu_assign_rate(tp, torch, sample, pri_c, cores, 10.0)
+        v_one, reps1 = cpu_assign_rate(tp, torch, sample[:4], pri_c, 1, 4.0)
+        torch.set_num_threads(cores)
+        cpu = {"value": v_all, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": "%d x the first 16 images of the cfg2 batch (~10 s) through oracle/torch_port.assign_batch (the reference's "
                          "per-image match loop restated in torch %s CPU, %d threads; the reference is Python and cannot travel)"
-                         % (reps, torch.__version__, cores)}
+                         % (reps, torch.__version__, cores),
+               "one_thread": {"value": v_one, "unit": "images/s", "cores": 1,
+                              "sample": "%d x the first 4 images, torch.set_num_threads(1)" % reps1},
+               "os_cpu_count": os.cpu_count(), "sched_getaffinity": cores,
+               "torch": torch.__version__}
+        try:
+            import torchvision
+            cpu["torchvision"] = torchvision.__version__
+        except Exception:
+            pass
 
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
+    rms = [x / K for x in rank_ms]
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2 training target assignment (match+encode): batch %d/GPU at 640x640, %d priors, "
                                "1..300 GT/image (mean %.1f), threshold 0.35, variances [0.1,0.2]" % (BATCH, P, mean_g),
-                   "global_batch": world * BATCH, "image": list(IMAGE), "priors": P, "parallelism": "image-sharded x%d, no collective; the global batch is the N=1 batch once per rank "
-                                  "(identical per-GPU work)" % world,
-                   "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2), one CUDA graph each"
-                         % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6)},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "phases": phases,
+                   "global_batch": world * BATCH, "image": list(IMAGE), "priors": P,
+                   "parallelism": "image-sharded x%d, no collective: each step's %d DISTINCT images (from one pool of %d = the cfg5 batch, "
+                                  "the same pool at every N) are cut into LPT shards of equal estimated cost" % (world, world * BATCH, POOL),
+                   "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2); steps replayed from CUDA graphs "
+                         "(one graph of %d steps while >= %d remain, single-step graphs for the rest)"
+                         % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6, SETS, SETS),
+                   "cpu_affinity": None if my_cpus is None else {"rank0_cpus": len(my_cpus), "visible": len(all_cpus)}},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode,
+        "cpu_baseline": cpu, "phases": phases, "cfg1": cfg1_info, "cfg4": cfg4_info,
         "detect": detect_info, "loss": loss_info, "cfg5_eval": cfg5_info,
-        "per_rank": {"ms_per_step": [x / K for x in rank_ms], "images_per_step": rank_images, "gt_per_step": rank_gt,
-                     "note": "value uses the slowest rank; shards are cut by estimated cost (sharding.local_targets)"},
+        "per_rank": {"ms_per_step": rms, "images_per_step": rank_images, "gt_per_step": rank_gt, "est_cost_per_step": rank_cost,
+                     "max_over_min_ms": max(rms) / min(rms),
+                     "note": "value uses the slowest rank; shards are LPT-packed by estimated cost (sharding.lpt_shards)"},
+        "shard_check": shard_check, "scaling_control": control,
     }
     emit(line)
     return 0

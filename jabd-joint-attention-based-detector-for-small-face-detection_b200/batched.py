@@ -110,7 +110,7 @@ def assign_targets(priors, targets, threshold=0.35, variances=(0.1, 0.2), label_
 
 
 def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000,
-           nms_thres=0.4, keep_topk=750, cluster=0, return_stats=False):
+           nms_thres=0.4, keep_topk=750, cluster=0, return_stats=False, out=None):
     """Fused decode -> class-1 score threshold -> top-k -> NMS -> keep for a batch.
 
     loc [B,P,4], conf [B,P,2] (softmax probabilities, R/nets/retinaface_eca_nonlocal.py:355-359),
@@ -118,6 +118,8 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
     Returns ``(dets [B,keep_topk,15] zero padded, counts [B] i32, keep_idx [B,keep_topk] i32, -1 padded)`` on the GPU.
     ``cluster``: CTAs (SMs) per image, 0 = automatic (``JABD_DET_CLUSTER``; results do not depend on it).
     ``return_stats`` adds the call's selection statistics ``[B,4]`` i32 (rounds, exact three-pass rounds, candidates, chunks).
+    ``out=(dets, counts, keep_idx)`` writes into existing contiguous CUDA tensors of those shapes (e.g. the send buffer of
+    ``sharding.DetectionGather``).
     """
     dev = _tensor.device_of(loc, conf, priors)
     loc_d, conf_d, pri = _tensor.to_dev(loc, dev), _tensor.to_dev(conf, dev), _tensor.to_dev(priors, dev)
@@ -131,9 +133,15 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
         raise ValueError("detect: expected loc [B,P,4], conf [B,P,2], landm [B,P,10], priors [P,4]")
     keep_cap = int(keep_topk) if keep_topk and keep_topk > 0 else P
     v0, v1 = _tensor.variances_of(variances)
-    dets = torch.empty((B, keep_cap, 15), dtype=torch.float32, device=dev)
-    counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    keep_idx = torch.empty((B, keep_cap), dtype=torch.int32, device=dev)
+    if out is not None:
+        dets, counts, keep_idx = out
+        for t, shp, dt in ((dets, (B, keep_cap, 15), torch.float32), (counts, (B,), torch.int32), (keep_idx, (B, keep_cap), torch.int32)):
+            if not (t.is_cuda and t.is_contiguous() and tuple(t.shape) == shp and t.dtype == dt):
+                raise ValueError("out must be contiguous CUDA tensors dets [B,keep,15] f32, counts [B] i32, keep_idx [B,keep] i32")
+    else:
+        dets = torch.empty((B, keep_cap, 15), dtype=torch.float32, device=dev)
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        keep_idx = torch.empty((B, keep_cap), dtype=torch.int32, device=dev)
     L = _lib.lib()
     ws = _tensor.workspace(L.jabd_detect_workspace_bytes(B, P, keep_cap), dev)
     with torch.cuda.device(dev):

@@ -150,6 +150,31 @@ def test_shard_bounds():
         assert bb[0] == 0 and bb[-1] == n and all(x <= y for x, y in zip(bb, bb[1:]))
 
 
+def test_lpt_shards():
+    """LPT bin packing over images: a partition, deterministic, tighter than the contiguous prefix split on ragged weights,
+    honours a per-rank item cap; gather_order is the permutation that undoes the rank-major concatenation."""
+    from jabd_b200 import sharding, synth
+    rng = np.random.default_rng(3)
+    for n, w in ((256, 8), (64, 2), (7, 4), (3, 4), (0, 2), (1, 1)):
+        wt = (1 + np.floor(299 * rng.random(n) ** 2)).tolist()
+        sh = sharding.lpt_shards(wt, w)
+        assert len(sh) == w and sorted(i for s in sh for i in s) == list(range(n)) and all(s == sorted(s) for s in sh)
+        assert sh == sharding.lpt_shards(list(wt), w)
+        perm = sharding.gather_order(sh)
+        assert sorted(perm) == list(range(n))
+    wt = sharding.image_costs(synth.make_gt_batch(2, 256, (640, 640)))
+    lpt = [sum(wt[i] for i in s) for s in sharding.lpt_shards(wt, 8)]
+    b = sharding.shard_bounds(256, 8, wt)
+    pre = [sum(wt[b[i]:b[i + 1]]) for i in range(8)]
+    assert max(lpt) / min(lpt) < 1.005 < max(pre) / min(pre)          # 256 ragged images: LPT is even to a fraction of a percent
+    capped = sharding.lpt_shards(wt, 8, max_items=32)
+    assert all(len(s) == 32 for s in capped)
+    with pytest.raises(ValueError):
+        sharding.lpt_shards([1.0] * 9, 2, max_items=4)
+    # equal weights: items keep their order, round-robin over the ranks
+    assert sharding.lpt_shards([1, 1, 1, 1, 1, 1], 3) == [[0, 3], [1, 4], [2, 5]]
+
+
 WORKER = r"""
 import os, sys
 sys.path.insert(0, %(root)r)
@@ -158,12 +183,38 @@ from jabd_b200 import sharding, synth
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
 targets = synth.make_gt_batch(2, 8, (640, 640))
-mine, (lo, hi) = sharding.local_targets(targets)
+mine, (lo, hi) = sharding.local_targets(targets, contiguous=True)
 # every rank derives the same partition; together the shards cover the batch once
 spans = [None, None]
 dist.all_gather_object(spans, (lo, hi))
 assert spans[0][0] == 0 and spans[0][1] == spans[1][0] and spans[1][1] == 8, spans
 assert [t.shape for t in mine] == [t.shape for t in targets[lo:hi]]
+# LPT shards (the default): index lists, every image in exactly one shard, same partition on every rank
+mine, idx = sharding.local_targets(targets)
+both = [None, None]
+dist.all_gather_object(both, idx)
+assert sorted(both[0] + both[1]) == list(range(8)) and both[rank] == idx
+assert [t.shape for t in mine] == [targets[i].shape for i in idx]
+shards = sharding.lpt_shards(sharding.image_costs(targets), 2)
+assert shards == both
+# side-stream gather object on CPU tensors (gloo): per-rank results come back in rank order; the permutation index restores
+# the global image order
+g = sharding.DetectionGather(len(idx) if len(both[0]) == len(both[1]) else 4, 3, "cpu", depth=2)
+if len(both[0]) == len(both[1]):
+    for slot in range(2):
+        g.dets(slot)[:] = torch.tensor(idx, dtype=torch.float32)[:, None, None] + 0.25 * slot
+        g.counts(slot)[:] = torch.tensor(idx, dtype=torch.int32) + 100
+        g.launch(slot)
+    for slot in range(2):
+        d, c = g.result(slot)
+        assert d.shape == (2, len(idx), 3, 15) and c.shape == (2, len(idx)) and c.dtype == torch.int32
+        perm = torch.tensor(sharding.gather_order(both))
+        glob = torch.empty(8)
+        glob[perm] = d[:, :, 0, 0].reshape(-1)
+        assert glob.tolist() == [i + 0.25 * slot for i in range(8)]
+        cg = torch.empty(8, dtype=torch.int32)
+        cg[perm] = c.reshape(-1)
+        assert cg.tolist() == [100 + i for i in range(8)]
 # fixed-shape all-gather of padded detections (CPU tensors -> gloo path)
 B_local, keep = 4, 6
 dets = torch.full((B_local, keep, 15), float(rank + 1))
