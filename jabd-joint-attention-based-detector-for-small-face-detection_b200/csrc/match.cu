@@ -229,13 +229,18 @@ struct ItemMeta {
 };
 
 struct MatchSmem {
-    GtRec gt[kStages][kSeg];          // bulk-copy destinations (kStages x 2 KB)
+    GtRec gt[kStages][kSeg + 1];      // bulk-copy destinations (kStages x 2 KB); record kSeg of every stage is the null GT
+                                      // (an inverted box far away: zero intersection with everything), never overwritten
     float4 pri[kStages][kTile];       //                        (kStages x 4 KB)
     float4 wbox[kStages][kTile / 32]; //                        (kStages x 128 B)
     ItemMeta meta[kStages];
     uint64_t full[kStages];           // producer -> consumers: item staged (transaction count)
     uint64_t empty[kStages];          // consumers -> producer: one arrival per consumer warp
+    uint32_t hits[kTile / 32][12];    // per consumer warp: the GT of the current 32-GT group that hit its bounding box, one
+                                      // byte each, padded with the null GT to a multiple of four (<= 36 bytes used)
 };
+constexpr int kNullGt = kSeg;         // index of the null GT record of a stage
+static_assert(kSeg + 1 <= 256, "hit lists hold GT indices as bytes");
 
 // One GT segment against the warp's 32 priors.  MODE 0: culled (ballot of 32 GT against the warp's bounding box),
 // MODE 1: dense, MODE 2: dense with torch.max's NaN / ordering semantics (malformed input).
@@ -244,7 +249,7 @@ struct MatchSmem {
 template <int MODE>
 __device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, int n, unsigned long long *rowkeys, float4 pb,
                                                 float area_p, float4 wbox, int p, bool valid, float &best, int &bidx,
-                                                bool &have_best)
+                                                bool &have_best, uint32_t *hits)
 {
     const unsigned lane = lane_id();
     if (MODE == 2) {
@@ -265,8 +270,7 @@ __device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, i
         return;
     }
     const uint32_t notp = 0xffffffffu - (uint32_t)p;
-    char *rowbase = reinterpret_cast<char *>(rowkeys);
-    asm volatile("" : "+l"(rowbase)); // keep the segment's key address materialised: one IMAD.WIDE per push
+    uint8_t *list = reinterpret_cast<uint8_t *>(hits);
     for (int base = 0; base < n; base += 32) {
         const int e = base + (int)lane;
         bool hit = e < n;
@@ -276,18 +280,23 @@ __device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, i
             const float h = fsub(fminf(a.w, wbox.w), fmaxf(a.y, wbox.y));
             hit = (w > 0.0f) && (h > 0.0f);
         }
-        unsigned m = __ballot_sync(kFull, hit);
-        while (m) {
-            // up to kWide hits per step; a short step repeats its last hit (re-evaluating a GT changes nothing:
-            // strict > for the column, max for the row)
+        const unsigned m = __ballot_sync(kFull, hit);
+        if (m == 0u) continue;
+        // the group's hits as a byte list in shared memory, padded with the null GT to a multiple of kWide: the steps below read
+        // four indices with one broadcast load and need neither bit scans nor a "repeat the last hit" fix-up
+        const int cnt = __popc(m);
+        if (hit) list[__popc(m & lanemask_lt())] = (uint8_t)e;
+        if (lane < (unsigned)(kWide - 1)) list[cnt + (int)lane] = (uint8_t)kNullGt;
+        __syncwarp();
+        for (int i = 0; i < cnt; i += kWide) {
+            const uint32_t four = hits[i >> 2];
             int j[kWide];
             float4 a[kWide];
             float aa[kWide];
             float v[kWide];
 #pragma unroll
             for (int k = 0; k < kWide; ++k) {
-                j[k] = (m || k == 0) ? base + __ffs(m) - 1 : j[k > 0 ? k - 1 : 0];
-                m &= m - 1; // no-op once m == 0
+                j[k] = (int)__byte_perm(four, 0u, 0x4440u + (unsigned)k);   // byte k, zero extended: one PRMT
                 a[k] = rec[j[k]].box;
                 aa[k] = rec[j[k]].area;
             }
@@ -300,16 +309,17 @@ __device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, i
             }
 #pragma unroll
             for (int k = 0; k < kWide; ++k) {
-                // column argmax: ascending GT index, strict > : ties keep the lowest index
+                // column argmax: ascending GT index, strict > : ties keep the lowest index (the null GT scores +0: never taken)
                 if (v[k] > best) { best = v[k]; bidx = j[k]; }
                 // row argmax: the warp's largest IoU for this GT; every lane that holds it (ties are rare) pushes its
-                // own key, the 64-bit max keeps the lowest prior index.  +0 / -0 / lanes past P never push.
-                const uint32_t bits = __float_as_uint(fmaxf(v[k], 0.0f));
+                // own key, the 64-bit max keeps the lowest prior index.  A well-formed pair has v >= +0, so the bit patterns
+                // order like the values; a warp whose best is +0 (no lane intersects this GT, or the null GT) pushes nothing.
+                const uint32_t bits = __float_as_uint(v[k]);
                 const uint32_t wmax = __reduce_max_sync(kFull, bits);
-                red_max_key(reinterpret_cast<unsigned long long *>(rowbase + ((unsigned)j[k] << 3)), bits | 0x80000000u, notp,
-                            bits == wmax && bits != 0u);
+                if (wmax != 0u) red_max_key(rowkeys + j[k], bits | 0x80000000u, notp, bits == wmax);
             }
         }
+        __syncwarp(); // every lane has read the list before the next group overwrites it
     }
 }
 
@@ -328,6 +338,14 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_k
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < kStages; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], kTile / 32); }
+    }
+    if (tid < kStages) {
+        GtRec null_rec;
+        null_rec.box = make_float4(1e30f, 1e30f, -1e30f, -1e30f);   // min(x2) - max(x1) is hugely negative against any box: inter = +0
+        null_rec.area = 1.0f;
+        null_rec.img_ok = 1;
+        null_rec.pad0 = null_rec.pad1 = 0;
+        s.gt[tid][kNullGt] = null_rec;
     }
     all_ok = __syncthreads_and(all_ok);
 
@@ -384,9 +402,9 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_k
         float best = 0.0f;
         int bidx = 0;
         bool have_best = false;
-        if (mode == 0) consume_segment<0>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
-        else if (mode == 1) consume_segment<1>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
-        else consume_segment<2>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best);
+        if (mode == 0) consume_segment<0>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best, s.hits[warp]);
+        else if (mode == 1) consume_segment<1>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best, s.hits[warp]);
+        else consume_segment<2>(rec, n, rowkeys, pb, area_p, wbox, p, valid, best, bidx, have_best, s.hits[warp]);
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.empty[slot]); // this warp no longer reads the stage
         // combine the segments of the image: max key = largest IoU, then lowest GT index
