@@ -11,12 +11,15 @@
 //                       (image, first GT, count, record offset) -- and the work-queue head.
 //   assign_match_kernel persistent CTAs (4 per SM) pull work items (prior tile, GT segment) from an atomic queue,
 //                       coarse-level tiles first (their large priors intersect most GT and make the longest items).
-//                       One elected thread runs a three-deep software pipeline: queue ticket for item i+3, work-list
-//                       entry for item i+2, and for item i+1 three bulk copies (cp.async.bulk + mbarrier: the GT
-//                       segment, the tile's 256 priors, its warp boxes) into the other half of a double buffer --
-//                       so that no global-memory latency is exposed between items.  Per item each warp tests 32 GT
-//                       per ballot against the bounding box of its 32 priors and visits only the hits, four per step
-//                       so that their loads and divisions overlap (one prior per lane).
+//                       One elected thread stages the next item while the eight consumer warps work on the current one:
+//                       as soon as a stage of the two-deep ring is free it draws a queue ticket, reads the work-list entry
+//                       and issues three bulk copies (cp.async.bulk + mbarrier: the GT segment, the tile's 256 priors,
+//                       its warp boxes).  A CTA thus never owns more than two items -- with a deeper ring the queue ran
+//                       empty while most CTAs still sat on a backlog nobody else could take, and the launch ended on
+//                       that backlog.  Per item each warp tests 32 GT per ballot against the bounding box of its 32
+//                       priors, compacts the hits into a byte list in shared memory (padded with a null GT record to a
+//                       multiple of four) and visits them four per step so that their loads and divisions overlap (one
+//                       prior per lane).
 //       column argmax   best GT per prior (overlaps.max(0), :120): in registers over the segment (ascending GT index,
 //                       strict >, so ties keep the lowest index), then one 64-bit atomicMax per prior on the packed key
 //                       (ordered IoU bits << 32 | ~GT index) to combine the segments.
@@ -48,7 +51,13 @@ constexpr int kTile = 256;       // priors per work item, one per thread
 constexpr int kSeg = JABD_KSEG;  // GT per work item (bounds the longest per-warp dependency chain)
 constexpr int kWide = 4;         // GT hits processed per step by a warp
 constexpr int kMatchCtasPerSm = 4;
-constexpr int kStages = 4;       // staged work items per CTA: consumer warps may run up to kStages-1 items apart
+#ifndef JABD_KSTAGES
+#define JABD_KSTAGES 2
+#endif
+constexpr int kStages = JABD_KSTAGES; // staged work items per CTA: consumer warps may run up to kStages-1 items apart.  Two, not more:
+                                     // what a CTA has staged it must finish itself, and once the queue is empty the launch lasts
+                                     // as long as the deepest backlog (4 stages + a prefetched ticket measured 23.3 us, 2 stages with
+                                     // the ticket drawn only when a stage is free 20.5 us)
 constexpr int kMatchThreads = kTile + 32; // 8 consumer warps + 1 producer warp
 
 struct __align__(32) GtRec {
@@ -350,13 +359,15 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_k
     all_ok = __syncthreads_and(all_ok);
 
     if (warp == kTile / 32) {
-        // ---- producer warp (one lane): queue ticket for item k+1 in flight while item k is resolved and staged
+        // ---- producer warp (one lane)
         if (tid != kTile) return;
         long long item = blockIdx.x;                      // the first item is static, the rest come from the queue
-        long long next = atomicAdd(&ws.ctl[1], 1);
         for (int k = 0;; ++k) {
             const int slot = k % kStages;
             if (k >= kStages) mbar_wait_relaxed(&s.empty[slot], (uint32_t)((k / kStages - 1) & 1));
+            // a ticket is drawn only when there is a free stage for it: a CTA never owns more than kStages items, so the tail of
+            // the launch (queue empty, CTAs finishing what they hold) is at most that deep
+            if (k > 0) item = atomicAdd(&ws.ctl[1], 1);
             ItemMeta m;
             m.tile = -1; m.image = m.c0 = m.n = m.rec0 = m.pad0 = m.pad1 = m.pad2 = 0;
             if (item >= n_items) { // queue drained: publish the sentinel and stop
@@ -373,8 +384,6 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_k
             bulk_g2s(s.gt[slot], ws.gtrec + seg.w, (uint32_t)seg.z * 32u, &s.full[slot]);
             bulk_g2s(s.pri[slot], priors + (size_t)tile * kTile, (uint32_t)np * 16u, &s.full[slot]);
             bulk_g2s(s.wbox[slot], ws.wbox + (size_t)tile * (kTile / 32), (kTile / 32) * 16u, &s.full[slot]);
-            item = next;
-            next = atomicAdd(&ws.ctl[1], 1);
         }
     }
 
