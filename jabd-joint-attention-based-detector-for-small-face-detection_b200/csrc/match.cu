@@ -4,7 +4,8 @@
 // (:93-162).  Three launches per batch, all on the caller's stream; nothing is allocated, there is no host
 // sync and no memset; the [G,P] IoU matrix is never stored.
 //
-//   assign_prep_kernel  image CTAs: GT rows -> 32-byte records (box, area, "image well formed" flag) in the
+//   assign_prep_kernel  image CTAs: GT rows -> 32-byte records (box, area, "image well formed" flag) for the match kernel and
+//                       64-byte records (whole row + "fast division is exact" flag) for the encode kernel in the
 //                       workspace, the image's row-argmax keys zeroed.  tile CTAs: per 256-prior tile a sanity flag,
 //                       the bounding box of each of its 8 warps' priors, the column-argmax keys of the tile zeroed
 //                       for every image.  one scan CTA: the work list -- every image's GT cut into segments of <= 64
@@ -28,8 +29,9 @@
 //                       (ordered IoU bits << 32 | ~prior index).
 //                       The largest key is the largest IoU and, among equal IoUs, the lowest index -- torch.max's
 //                       first-maximum rule -- so indices match the reference bit for bit.
-//   match_encode_kernel one CTA per (image, tile): unpack the keys, force-match (:127-130, largest j wins), gather
-//                       of the matched GT row, threshold (:143), encode (:61-84), coalesced stores.
+//   match_encode_kernel one CTA per (256-prior tile, 8 consecutive images): force-match scan (:127-130, largest j wins), then per
+//                       image a software pipeline -- unpack the column key, gather the matched GT's 64-byte record, threshold
+//                       (:143), encode (:61-84), coalesced stores -- with the next images' keys and records in flight.
 //
 // Why culling is exact: with well-formed inputs (finite coordinates, GT area in [0, 2^40], prior area in
 // [2^-40, 2^40]) every IoU is >= +0 and a pair whose boxes do not intersect has IoU == +0 exactly, which can
@@ -67,8 +69,20 @@ struct __align__(32) GtRec {
     int pad0, pad1;
 };
 
+// What the encode kernel gathers for a prior's matched GT: the whole row as ONE aligned 64-byte record (four 16-byte
+// loads instead of fifteen scalar ones) plus the verdict of the range test that lets every division of that row take
+// the shared-reciprocal fast path (see match_encode_kernel).
+struct __align__(64) EncRec {
+    float4 box;     // x1 y1 x2 y2
+    float lm[10];   // five landmark points
+    float label;
+    int fast_ok;    // all 14 coordinates finite with magnitude <= 2^59, x2-x1 and y2-y1 within [2^-60, 2^60]
+};
+static_assert(sizeof(EncRec) == 64, "EncRec is one 64-byte record");
+
 struct AssignWorkspace {
     GtRec *gtrec;               // [sumG]
+    EncRec *encrec;             // [sumG]
     unsigned long long *rowkey; // [sumG] best prior per GT (0 = value +0 at prior 0)
     unsigned long long *colkey; // [B,P]  best GT per prior before the force-match override (0 = value +0 at GT 0)
     float4 *wbox;               // [n_tiles*8] bounding box of each warp's 32 priors (point form)
@@ -89,6 +103,7 @@ static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *
     const size_t nt = (size_t)((P + kTile - 1) / kTile) + 1;
     const size_t nseg = (size_t)(B > 0 ? B : 0) + (size_t)(sumG > 0 ? sumG : 0) / kSeg + 1;
     size_t o_rec = take(sizeof(GtRec) * ng);
+    size_t o_enc = take(sizeof(EncRec) * ng);
     size_t o_row = take(sizeof(unsigned long long) * ng);
     size_t o_col = take(sizeof(unsigned long long) * (size_t)B * (size_t)P);
     size_t o_wbox = take(sizeof(float4) * nt * (kTile / 32));
@@ -97,6 +112,7 @@ static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *
     size_t o_ctl = take(sizeof(int) * 4);
     if (w) {
         w->gtrec = reinterpret_cast<GtRec *>(base + o_rec);
+        w->encrec = reinterpret_cast<EncRec *>(base + o_enc);
         w->rowkey = reinterpret_cast<unsigned long long *>(base + o_row);
         w->colkey = reinterpret_cast<unsigned long long *>(base + o_col);
         w->wbox = reinterpret_cast<float4 *>(base + o_wbox);
@@ -121,23 +137,42 @@ __global__ void __launch_bounds__(kTile) assign_prep_kernel(const float *__restr
         const int b = blockIdx.x;
         const int g0 = gt_off[b];
         const int G = gt_off[b + 1] - g0;
+        // one pass over the rows (one load round trip): everything but the "whole image well formed" flag, which needs the
+        // CTA's vote, is written at once; the flag follows after the barrier
         int ok = 1;
+        float area0 = 0.0f; // area of this thread's first row (G <= kTile: its only one)
         for (int g = tid; g < G; g += kTile) {
             const float *r = gt + (size_t)(g0 + g) * JABD_GT_ROW;
-            const float4 a = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-            const float aa = box_area(a);
-            ok &= (aa >= 0.0f && aa <= 0x1p40f) ? 1 : 0; // false for NaN / inf coordinates too
+            float v[JABD_GT_ROW];
+#pragma unroll
+            for (int k = 0; k < JABD_GT_ROW; ++k) v[k] = __ldg(r + k);
+            const float4 box = make_float4(v[0], v[1], v[2], v[3]);
+            const float area = box_area(box);
+            ok &= (area >= 0.0f && area <= 0x1p40f) ? 1 : 0; // false for NaN / inf coordinates too
+            if (g == tid) area0 = area;
+            ws.gtrec[g0 + g].box = box;
+            ws.rowkey[g0 + g] = 0ull;
+            float mx = 0.0f;
+            bool finite = true;
+#pragma unroll
+            for (int k = 0; k < JABD_GT_ROW - 1; ++k) {
+                mx = fmaxf(mx, fabsf(v[k]));       // fmaxf drops a NaN operand, hence the separate test
+                finite = finite && (v[k] == v[k]);
+            }
+            const float nw = fsub(v[2], v[0]), nh = fsub(v[3], v[1]);
+            const int fast_ok = (finite && mx <= 0x1p59f && nw >= 0x1p-60f && nw <= 0x1p60f && nh >= 0x1p-60f && nh <= 0x1p60f) ? 1 : 0;
+            float4 *e = reinterpret_cast<float4 *>(ws.encrec + g0 + g);
+            e[0] = box;
+            e[1] = make_float4(v[4], v[5], v[6], v[7]);
+            e[2] = make_float4(v[8], v[9], v[10], v[11]);
+            e[3] = make_float4(v[12], v[13], v[14], __int_as_float(fast_ok));
         }
         ok = __syncthreads_and(ok);
         for (int g = tid; g < G; g += kTile) {
-            const float *r = gt + (size_t)(g0 + g) * JABD_GT_ROW;
-            GtRec rec;
-            rec.box = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-            rec.area = box_area(rec.box);
-            rec.img_ok = ok;
-            rec.pad0 = rec.pad1 = 0;
-            ws.gtrec[g0 + g] = rec;
-            ws.rowkey[g0 + g] = 0ull;
+            float area = area0;
+            if (g != tid) area = box_area(ws.gtrec[g0 + g].box); // this thread's own store
+            // second half of the record: area, img_ok, padding
+            reinterpret_cast<float4 *>(ws.gtrec + g0 + g)[1] = make_float4(area, __int_as_float(ok), 0.0f, 0.0f);
         }
         return;
     }
@@ -441,127 +476,263 @@ struct EncodeArgs {
     float *out_bpo;
 };
 
-__global__ void __launch_bounds__(kTile) match_encode_kernel(EncodeArgs a, AssignWorkspace ws)
-{
-    __shared__ int s_forced[kTile];
-    __shared__ __align__(16) float s_lm[kTile * 10];
-    const int b = blockIdx.y;
-    const int tid = threadIdx.x;
-    const int p0 = blockIdx.x * kTile;
-    const int p = p0 + tid;
-    const int P = a.P;
-    const bool valid = p < P;
-    const int n_valid = (P - p0) < kTile ? (P - p0) : kTile;
-    const int g0 = a.gt_off[b];
-    const int G = a.gt_off[b + 1] - g0;
-    const size_t row = (size_t)b * P + p;
+// One CTA = kEncThreads consecutive priors (one per thread) x kEncImages consecutive images.  What depends on the prior alone
+// (five refined reciprocals, the range test) is computed once per thread; the images are then encoded in a software pipeline:
+// while image i is being encoded the matched GT record of image i+1 is already in flight (one aligned 64-byte EncRec, four
+// 16-byte loads) and the column keys of images i+2, i+3 are being fetched.  The force-match scan of all the CTA's images runs
+// once, before the loop, between the CTA's only two barriers.
+//
+// Divisions.  16 IEEE quotients per prior and image share 5 divisors (var0*w, var0*h for the centre and the ten landmark
+// coordinates; w, h for the size ratio; var1) -- one refined reciprocal each (fdiv_fast).  The fast quotient is the bits of
+// div.rn when the divisor's magnitude lies in [2^-60, 2^60] and the numerator is zero or lies in that range.  That is
+// established ONCE per prior and once per GT row instead of per quotient:
+//   * prior:  |cx|, |cy|, w, h, var0*w, var0*h within [2^-36, 2^59] (prior_ok), var1 within [2^-60, 2^60];
+//   * GT row (EncRec.fast_ok, assign_prep_kernel): 14 finite coordinates of magnitude <= 2^59, x2-x1 and y2-y1 in [2^-60, 2^60].
+//   Then every numerator  t - c  (t a GT coordinate or box centre, |t| <= 2^59; c = cx or cy, 2^-36 <= |c| <= 2^59) is at most
+//   2^60, and if it is not zero it is at least 2^-60: either |t| < |c|/2 and the difference exceeds |c|/2 >= 2^-37, or both are
+//   multiples of ulp(2^-37) = 2^-60 and so is their exact difference.  t - c is never -0 (c != 0).  The size ratios are normal
+//   positive numbers, their logarithms are zero or of magnitude in [2^-25, 2^7].
+// A row or prior that fails takes the compiler's generic divide (bit-identical results, tests force both paths).
+#ifndef JABD_ENC_THREADS
+#define JABD_ENC_THREADS 256
+#endif
+#ifndef JABD_ENC_IMAGES
+#define JABD_ENC_IMAGES 8
+#endif
+#ifndef JABD_ENC_MINB
+#define JABD_ENC_MINB 1
+#endif
+constexpr int kEncThreads = JABD_ENC_THREADS;
+constexpr int kEncImages = JABD_ENC_IMAGES;
+constexpr int kEncScan = 4;                   // row keys per thread in flight during the force-match scan
 
-    // issued before the barriers so that their latency overlaps the force-match scan
-    unsigned long long ck = 0ull; // 0: no positive IoU, i.e. value +0 at GT 0
-    float4 pr = make_float4(0.f, 0.f, 1.f, 1.f);
-    if (valid) {
-        ck = ws.colkey[row];
-        pr = __ldg(a.priors + p);
-    }
-    s_forced[tid] = -1;
-    __syncthreads();
-    // force-match: best_truth_idx[best_prior_idx[j]] = j for j ascending -> the largest j wins (:129-130)
-    for (int g = tid; g < G; g += kTile) {
-        const unsigned long long key = ws.rowkey[g0 + g]; // 0: no positive IoU, i.e. value +0 at prior 0
-        const uint32_t bp = key ? key_idx(key) : 0u;
-        if (bp >= (uint32_t)p0 && bp < (uint32_t)(p0 + kTile)) atomicMax(&s_forced[bp - p0], g);
-        if (blockIdx.x == 0) {
-            if (a.out_bpi) a.out_bpi[g0 + g] = (int)bp;
-            if (a.out_bpo) a.out_bpo[g0 + g] = key ? ord_inv(key_ord(key)) : 0.0f;
-        }
-    }
-    __syncthreads();
+struct EncRow {   // the GT a prior is matched with in one image
+    float4 e0, e1, e2, e3;   // its EncRec
+    int idx;
+    float ov;
+};
 
-    float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
-    long long conf = 0;
+// Per-thread constants of the encode loop.
+struct EncPrior {
+    float4 pr;
+    float dx, dy, rdx, rdy, rw, rh, rv;
+    bool ok;
+};
+
+struct EncOut {   // one prior's targets for one image
+    float4 loc;
+    long long conf;
     float lm[10];
+    int idx;
+    float ov;
+};
+
+// kLandm: landm_t requested; kEncode: SSD encode (else raw matched boxes, match_iou); kExtra: label_mode / the optional
+// best_truth_* outputs are looked at (the MultiBoxLoss path compiles without them).
+template <bool kLandm, bool kEncode, bool kExtra>
+__device__ __forceinline__ EncOut encode_compute(const EncodeArgs &a, const EncPrior &q, const EncRow &r, bool has_gt)
+{
+    EncOut o;
+    const float4 m = r.e0;
+    float c = r.e3.z;
+    if (kExtra && a.label_mode) c = fadd(c, 1.0f); // R/utils/box_utils.py:315
+    if (r.ov < a.threshold) c = 0.0f;              // :143
+    o.conf = (long long)c;                         // float -> int64 store truncates
+    o.idx = r.idx;
+    o.ov = r.ov;
+    const bool fast = q.ok && __float_as_int(r.e3.w) != 0;
+    o.loc = m;
+    float nl[10];
+    if (kLandm) {
+        const float t[10] = {r.e1.x, r.e1.y, r.e1.z, r.e1.w, r.e2.x, r.e2.y, r.e2.z, r.e2.w, r.e3.x, r.e3.y};
 #pragma unroll
-    for (int k = 0; k < 10; ++k) lm[k] = 0.0f;
-    int idx = 0;
-    float ov = 0.0f;
-    if (valid && G > 0) {
-        if (ck) { idx = (int)key_idx(ck); ov = ord_inv(key_ord(ck)); }
-        const int f = s_forced[tid];
-        if (f >= 0) { idx = f; ov = 2.0f; } // :127
-        const float *r = a.gt + (size_t)(g0 + idx) * JABD_GT_ROW;
-        const float4 m = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3));
-        float c = __ldg(r + 14);
-        if (a.label_mode) c = fadd(c, 1.0f);       // R/utils/box_utils.py:315
-        if (ov < a.threshold) c = 0.0f;            // :143
-        conf = (long long)c;                       // float -> int64 store truncates
-        // 16 IEEE divisions per prior share 5 divisors: var0*w, var0*h (centre + 10 landmark coordinates), w, h
-        // (size ratio) and var1 -- one refined reciprocal each (fdiv_fast).  The fast quotient equals div.rn when
-        // divisor and numerator magnitudes lie in [2^-60, 2^60]; one flag collects that for all of them (an exactly
-        // zero numerator counts as out of range) and the rare thread that fails redoes its row with the generic divide.
-        const float dx = fmul(a.var0, pr.z), dy = fmul(a.var0, pr.w);
-        bool fast = mag_safe(dx) && mag_safe(dy) && mag_safe(pr.z) && mag_safe(pr.w) && mag_safe(a.var1);
-        const float rdx = rcp_refined(dx), rdy = rcp_refined(dy);
-        const float ncx = fsub(fmul(fadd(m.x, m.z), 0.5f), pr.x), ncy = fsub(fmul(fadd(m.y, m.w), 0.5f), pr.y);
-        float nl[10];
-        if (a.landm_t) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                nl[2 * k] = fsub(__ldg(r + 4 + 2 * k), pr.x);
-                nl[2 * k + 1] = fsub(__ldg(r + 5 + 2 * k), pr.y);
-                fast = fast && mag_safe(nl[2 * k]) && mag_safe(nl[2 * k + 1]);
-                lm[2 * k] = fdiv_fast(nl[2 * k], dx, rdx);
-                lm[2 * k + 1] = fdiv_fast(nl[2 * k + 1], dy, rdy);
-            }
-        }
-        if (a.encode_mode) {
-            const float rw = rcp_refined(pr.z), rh = rcp_refined(pr.w), rv = rcp_refined(a.var1);
-            const float nw = fsub(m.z, m.x), nh = fsub(m.w, m.y);
-            fast = fast && mag_safe(ncx) && mag_safe(ncy) && mag_safe(nw) && mag_safe(nh);
-            loc.x = fdiv_fast(ncx, dx, rdx);
-            loc.y = fdiv_fast(ncy, dy, rdy);
-            const float lw = log_f32(fdiv_fast(nw, pr.z, rw)), lh = log_f32(fdiv_fast(nh, pr.w, rh));
-            fast = fast && mag_safe(lw) && mag_safe(lh);
-            loc.z = fdiv_fast(lw, a.var1, rv);
-            loc.w = fdiv_fast(lh, a.var1, rv);
-        } else {
-            loc = m;
-        }
-        if (!fast) {
-            loc = a.encode_mode ? encode_box(m, pr, a.var0, a.var1) : m;
-            if (a.landm_t) {
-#pragma unroll
-                for (int k = 0; k < 10; ++k) lm[k] = fdiv(nl[k], (k & 1) ? dy : dx);
-            }
+        for (int k = 0; k < 5; ++k) {
+            nl[2 * k] = fsub(t[2 * k], q.pr.x);
+            nl[2 * k + 1] = fsub(t[2 * k + 1], q.pr.y);
+            o.lm[2 * k] = fdiv_fast(nl[2 * k], q.dx, q.rdx);
+            o.lm[2 * k + 1] = fdiv_fast(nl[2 * k + 1], q.dy, q.rdy);
         }
     }
+    if (kEncode) {
+        const float ncx = fsub(fmul(fadd(m.x, m.z), 0.5f), q.pr.x), ncy = fsub(fmul(fadd(m.y, m.w), 0.5f), q.pr.y);
+        const float nw = fsub(m.z, m.x), nh = fsub(m.w, m.y);
+        o.loc.x = fdiv_fast(ncx, q.dx, q.rdx);
+        o.loc.y = fdiv_fast(ncy, q.dy, q.rdy);
+        const float lw = log_f32(fdiv_fast(nw, q.pr.z, q.rw)), lh = log_f32(fdiv_fast(nh, q.pr.w, q.rh));
+        o.loc.z = fdiv_fast(lw, a.var1, q.rv);
+        o.loc.w = fdiv_fast(lh, a.var1, q.rv);
+    }
+    if (!fast) {
+        if (kEncode) o.loc = encode_box(m, q.pr, a.var0, a.var1);
+        if (kLandm) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) o.lm[k] = fdiv(nl[k], (k & 1) ? q.dy : q.dx);
+        }
+    }
+    if (!has_gt) { // an image without GT: all-zero targets (the reference's freshly allocated rows stay untouched)
+        o.loc = make_float4(0.f, 0.f, 0.f, 0.f);
+        o.conf = 0;
+        o.idx = 0;
+        o.ov = 0.0f;
+        if (kLandm) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) o.lm[k] = 0.0f;
+        }
+    }
+    return o;
+}
+
+template <bool kLandm, bool kExtra>
+__device__ __forceinline__ void encode_store(const EncodeArgs &a, const EncOut &o, size_t row, size_t wrow, bool valid, bool vec_ok,
+                                             int n_valid, float *sl, unsigned lane)
+{
     if (valid) {
-        a.loc_t[row] = loc;
-        a.conf_t[row] = conf;
-        if (a.out_bti) a.out_bti[row] = idx;
-        if (a.out_bto) a.out_bto[row] = ov;
-    }
-    if (a.landm_t) {
-        // [tile,10] rows through shared memory so the global stores are contiguous 16-byte vectors
-#pragma unroll
-        for (int k = 0; k < 10; ++k) s_lm[tid * 10 + k] = lm[k];
-        __syncthreads();
-        float *dst = a.landm_t + ((size_t)b * P + p0) * 10;
-        const int nf = n_valid * 10;
-        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-            float4 *d4 = reinterpret_cast<float4 *>(dst);
-            const float4 *s4 = reinterpret_cast<const float4 *>(s_lm);
-            if (n_valid == kTile) { // full tile: 640 vectors, 2.5 per thread
-                d4[tid] = s4[tid];
-                d4[tid + kTile] = s4[tid + kTile];
-                if (tid < kTile / 2) d4[tid + 2 * kTile] = s4[tid + 2 * kTile];
-            } else {
-                const int n4 = nf >> 2;
-                for (int i = tid; i < n4; i += kTile) d4[i] = s4[i];
-                for (int i = (n4 << 2) + tid; i < nf; i += kTile) dst[i] = s_lm[i];
-            }
-        } else {
-            for (int i = tid; i < nf; i += kTile) dst[i] = s_lm[i];
+        a.loc_t[row] = o.loc;
+        a.conf_t[row] = o.conf;
+        if (kExtra) {
+            if (a.out_bti) a.out_bti[row] = o.idx;
+            if (a.out_bto) a.out_bto[row] = o.ov;
         }
+    }
+    if (kLandm) {
+        // the warp's [32,10] rows through shared memory so that the global stores are contiguous 16-byte vectors
+        __syncwarp(); // the previous image's rows have been read
+#pragma unroll
+        for (int k = 0; k < 10; k += 2) *reinterpret_cast<float2 *>(sl + lane * 10 + k) = make_float2(o.lm[k], o.lm[k + 1]);
+        __syncwarp();
+        float *dst = a.landm_t + wrow * 10;
+        if (vec_ok && (wrow & 1) == 0) { // 80 aligned vectors, 2.5 per lane
+            float4 *d4 = reinterpret_cast<float4 *>(dst);
+            const float4 *s4 = reinterpret_cast<const float4 *>(sl);
+            d4[lane] = s4[lane];
+            d4[lane + 32] = s4[lane + 32];
+            if (lane < 16) d4[lane + 64] = s4[lane + 64];
+        } else {
+            for (int j = (int)lane; j < n_valid * 10; j += 32) dst[j] = sl[j];
+        }
+    }
+}
+
+template <bool kLandm, bool kEncode, bool kExtra>
+__global__ void __launch_bounds__(kEncThreads, JABD_ENC_MINB) match_encode_kernel(EncodeArgs a, AssignWorkspace ws, int B)
+{
+    __shared__ int s_off[kEncImages + 1];
+    __shared__ int s_forced[kEncImages][kEncThreads];
+    __shared__ __align__(16) float s_lm[kLandm ? kEncThreads * 10 : 4];   // 320 per warp
+
+    const int tid = threadIdx.x;
+    const unsigned lane = lane_id();
+    const int P = a.P;
+    const int p0 = blockIdx.x * kEncThreads;
+    const int wp0 = p0 + (tid & ~31);                  // first prior of this warp
+    const int p = p0 + tid;
+    const bool valid = p < P;
+    const int b0 = blockIdx.y * kEncImages;
+    const int nb = (B - b0) < kEncImages ? (B - b0) : kEncImages;
+
+    if (tid <= kEncImages) s_off[tid] = a.gt_off[b0 + (tid < nb ? tid : nb)];
+    // column keys (0: no positive IoU, i.e. value +0 at GT 0) of the first two images
+    const unsigned long long *ckp = ws.colkey + (size_t)b0 * P + (valid ? p : 0);
+    unsigned long long ck0 = ckp[0];
+    unsigned long long ck1 = nb > 1 ? ckp[P] : 0ull;
+#pragma unroll
+    for (int i = 0; i < kEncImages; ++i) s_forced[i][tid] = -1;
+    EncPrior q;
+    q.pr = __ldg(a.priors + (valid ? p : 0));
+    __syncthreads();
+
+    // force-match: best_truth_idx[best_prior_idx[j]] = j for j ascending -> the largest j wins (:129-130).  The row keys of
+    // the CTA's images are contiguous; every thread takes kEncScan of them per round, all loads of a round in flight together.
+    // (Encoding speculatively by the column argmax while the scan is in flight, and the few forced priors again at the end,
+    // was measured: the extra barriers and the second pass cost more than the round trip they hide, 11.5 vs 10.9 us.)
+    {
+        int off[kEncImages + 1];
+#pragma unroll
+        for (int i = 0; i <= kEncImages; ++i) off[i] = s_off[i];
+        const int gtot = off[kEncImages] - off[0];
+        for (int base = 0; base < gtot; base += kEncScan * kEncThreads) {
+            unsigned long long rk[kEncScan];
+#pragma unroll
+            for (int k = 0; k < kEncScan; ++k) {
+                const int g = base + k * kEncThreads + tid;
+                rk[k] = (g < gtot) ? ws.rowkey[off[0] + g] : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < kEncScan; ++k) {
+                const int g = off[0] + base + k * kEncThreads + tid;
+                if (g < off[kEncImages]) {
+                    int img = 0;
+#pragma unroll
+                    for (int i = 1; i < kEncImages; ++i) img += (g >= off[i]) ? 1 : 0;
+                    const unsigned long long key = rk[k];                             // 0: no positive IoU, i.e. value +0 at prior 0
+                    const uint32_t bp = key ? key_idx(key) : 0u;
+                    if (bp - (uint32_t)p0 < (uint32_t)kEncThreads) atomicMax(&s_forced[img][bp - (uint32_t)p0], g - s_off[img]);
+                    if (kExtra && p0 == 0) {
+                        if (a.out_bpi) a.out_bpi[g] = (int)bp;
+                        if (a.out_bpo) a.out_bpo[g] = key ? ord_inv(key_ord(key)) : 0.0f;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (wp0 >= P) return;
+
+    // the GT row a prior is matched with in image i: the forced one if any, else its column argmax
+    auto fetch = [&](int i, unsigned long long key) {
+        EncRow r;
+        r.idx = 0;
+        r.ov = 0.0f;
+        if (key) { r.idx = (int)key_idx(key); r.ov = ord_inv(key_ord(key)); }
+        const int f = s_forced[i][tid];
+        if (f >= 0) { r.idx = f; r.ov = 2.0f; }    // :127
+        // (an image without GT: the record belongs to the next image or is the workspace's spare one -- loaded, never used)
+        const float4 *e = reinterpret_cast<const float4 *>(ws.encrec + s_off[i] + r.idx);
+        r.e0 = __ldg(e); r.e1 = __ldg(e + 1); r.e2 = __ldg(e + 2); r.e3 = __ldg(e + 3);
+        return r;
+    };
+    EncRow r0 = fetch(0, ck0), r1 = r0;
+    if (nb > 1) r1 = fetch(1, ck1);
+    unsigned long long cka = nb > 2 ? ckp[(size_t)2 * P] : 0ull, ckb = nb > 3 ? ckp[(size_t)3 * P] : 0ull; // images i+2, i+3
+
+    auto prior_consts = [&](EncPrior &c) {
+        c.dx = fmul(a.var0, c.pr.z);
+        c.dy = fmul(a.var0, c.pr.w);
+        const float4 pr = c.pr;
+        const float lo = fminf(fminf(fminf(fabsf(pr.x), fabsf(pr.y)), fminf(fabsf(pr.z), fabsf(pr.w))), fminf(fabsf(c.dx), fabsf(c.dy)));
+        const float hi = fmaxf(fmaxf(fmaxf(fabsf(pr.x), fabsf(pr.y)), fmaxf(fabsf(pr.z), fabsf(pr.w))), fmaxf(fabsf(c.dx), fabsf(c.dy)));
+        // fminf/fmaxf drop a NaN operand, hence the explicit NaN tests
+        c.ok = lo >= 0x1p-36f && hi <= 0x1p59f && (pr.x == pr.x) && (pr.y == pr.y) && (pr.z == pr.z) && (pr.w == pr.w) && mag_safe(a.var1);
+        c.rdx = rcp_refined(c.dx);
+        c.rdy = rcp_refined(c.dy);
+        c.rw = rcp_refined(c.pr.z);
+        c.rh = rcp_refined(c.pr.w);
+        c.rv = rcp_refined(a.var1);
+    };
+    prior_consts(q);
+    float *sl = s_lm + (kLandm ? (tid & ~31) * 10 : 0);
+    const int n_valid = (P - wp0) < 32 ? (P - wp0) : 32;
+    const bool vec_ok = n_valid == 32 && (reinterpret_cast<uintptr_t>(a.landm_t) & 15u) == 0;
+
+    // Two images per trip; r0 / r1 alternate, no register rotation.  Order within a trip: encode image i, REQUEST the record of
+    // image i+2, only then store image i -- a request queued behind a burst of stores (every warp of the SM stores at about the
+    // same time, and the SM's path to L2 carries 32 bytes per clock) would come back after the next image's arithmetic is done.
+    size_t row = (size_t)b0 * P + p, wrow = (size_t)b0 * P + wp0;
+#pragma unroll 1
+    for (int i = 0; i < nb; i += 2) {
+        const EncOut o0 = encode_compute<kLandm, kEncode, kExtra>(a, q, r0, s_off[i + 1] > s_off[i]);
+        const unsigned long long ck4 = (i + 4 < nb) ? ckp[(size_t)(i + 4) * P] : 0ull;
+        const unsigned long long ck5 = (i + 5 < nb) ? ckp[(size_t)(i + 5) * P] : 0ull;
+        if (i + 2 < nb) r0 = fetch(i + 2, cka);
+        encode_store<kLandm, kExtra>(a, o0, row, wrow, valid, vec_ok, n_valid, sl, lane);
+        if (i + 1 >= nb) break;
+        row += P; wrow += P;
+        const EncOut o1 = encode_compute<kLandm, kEncode, kExtra>(a, q, r1, s_off[i + 2] > s_off[i + 1]);
+        if (i + 3 < nb) r1 = fetch(i + 3, ckb);
+        encode_store<kLandm, kExtra>(a, o1, row, wrow, valid, vec_ok, n_valid, sl, lane);
+        row += P; wrow += P;
+        cka = ck4;
+        ckb = ck5;
     }
 }
 
@@ -656,8 +827,19 @@ int jabd_assign_encode(const float *priors, int64_t P, const float *gt, const in
     a.out_bto = best_truth_overlap;
     a.out_bpi = best_prior_idx;
     a.out_bpo = best_prior_overlap;
-    const dim3 grid((unsigned)((P + kTile - 1) / kTile), (unsigned)B);
-    match_encode_kernel<<<grid, kTile, 0, st>>>(a, ws);
+    const dim3 grid((unsigned)((P + kEncThreads - 1) / kEncThreads), (unsigned)((B + kEncImages - 1) / kEncImages));
+    const bool extra = label_mode != 0 || best_truth_idx || best_truth_overlap || best_prior_idx || best_prior_overlap;
+    const int variant = (landm_t ? 4 : 0) | (encode_mode ? 2 : 0) | (extra ? 1 : 0);
+    switch (variant) {
+    case 0: match_encode_kernel<false, false, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    case 1: match_encode_kernel<false, false, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    case 2: match_encode_kernel<false, true, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    case 3: match_encode_kernel<false, true, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    case 4: match_encode_kernel<true, false, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    case 5: match_encode_kernel<true, false, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    case 6: match_encode_kernel<true, true, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    default: match_encode_kernel<true, true, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    }
     JABD_LAUNCH_CHECK("match_encode_kernel");
     return JABD_OK;
 }
