@@ -749,59 +749,85 @@ def main():
         pr5 = anchors.cached_priors(config.cfg_mnet, size, dev)
         loc5, conf5, lm5 = (x.to(dev) for x in clustered_preds(5, size, pr5, rank * B5, B5, count=40))   # resident in HBM
         post5 = torch.from_numpy(batched.letterbox_params(size, [size] * B5)).to(dev)
-        gather = sharding.DetectionGather(B5, keep5, dev, depth=2)
         kidx5 = torch.empty((B5, keep5), dtype=torch.int32, device=dev)
-
-        def cfg5_step(k, overlap=True):
-            slot = k & 1
-            if k >= 2:
-                gather.result(slot)         # this slot's previous gather must have drained before its buffers are refilled
-            d, c = gather.dets(slot), gather.counts(slot)
-            batched.detect(loc5, conf5, lm5, pr5, VAR, keep_topk=keep5, out=(d, c, kidx5))
-            batched.correct_boxes(d, c, post5, letterbox=False, to_pixels=True)
-            gather.launch(slot)
-            if not overlap:
-                gather.result(slot)         # serialised variant: the step's stream waits for its own gather
-        for k in range(4):
-            cfg5_step(k)
         n5 = 20
 
-        def cfg5_loop(overlap):
-            def body(k):
-                cfg5_step(k, overlap)
-                if k == n5 - 1:             # drain inside the timed region: the last gathers are part of the K steps
-                    gather.result((k - 1) & 1)
-                    gather.result(k & 1)
-            ms_, _ = timed_loop(body, n5)
-            return ms_
-        ms5 = cfg5_loop(True)
-        ms5_serial = cfg5_loop(False)
-        gd, gc = gather.result((n5 - 1) & 1)
-        torch.cuda.synchronize(dev)
-        # the collective alone, back to back
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for k in range(n5):
-            gather.launch(k & 1)
-            gather.result(k & 1)
-        e1.record()
-        barrier()
-        us_ag = max_over_ranks(e0.elapsed_time(e1)) / n5 * 1e3
+        def cfg5_measure(gather):
+            """detect -> pixel scaling -> exchange, per step; in the overlapped flow the consumer side of batch k-1 (result: the
+            gathered rows become visible on this stream) runs while batch k is exchanged."""
+            depth = gather.depth
+
+            def step(k, overlap=True):
+                slot = k % depth
+                gather.acquire(slot)        # the slot's previous exchange has read its send buffer
+                d, c = gather.dets(slot), gather.counts(slot)
+                batched.detect(loc5, conf5, lm5, pr5, VAR, keep_topk=keep5, out=(d, c, kidx5))
+                batched.correct_boxes(d, c, post5, letterbox=False, to_pixels=True)
+                gather.launch(slot)
+                if not overlap:
+                    gather.result(slot)     # serialised variant: the step's stream waits for its own exchange
+                elif k >= 1:
+                    gather.result((k - 1) % depth)
+            for k in range(2 * depth):
+                step(k)
+            gather.result((2 * depth - 1) % depth)
+
+            def loop(overlap):
+                def body(k):
+                    step(k, overlap)
+                    if k == n5 - 1:         # drain inside the timed region: the last exchange is part of the K steps
+                        gather.result(k % depth)
+                ms_, _ = timed_loop(body, n5)
+                return ms_
+            ms_o = loop(True)
+            ms_s = loop(False)
+            gd_, gc_ = gather.result((n5 - 1) % depth)
+            torch.cuda.synchronize(dev)
+            # the exchange alone, back to back
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for k in range(n5):
+                gather.acquire(k % depth)
+                gather.launch(k % depth)
+                gather.result(k % depth)
+            e1.record()
+            barrier()
+            us = max_over_ranks(e0.elapsed_time(e1)) / n5 * 1e3
+            return ms_o, ms_s, us, gd_, gc_
+
+        gather = sharding.PeerGather(B5, keep5, dev, depth=3)
+        ms5, ms5_serial, us_ag, gd, gc = cfg5_measure(gather)
+        gd, gc = gd.clone(), gc.clone()
+        p2p_status = gather.status()
+        assert p2p_status == 0, "a peer-memory wait timed out (status %d)" % p2p_status
+        nccl_ctl = None
+        if world > 1:
+            g_nccl = sharding.DetectionGather(B5, keep5, dev, depth=2)
+            ms_n, ms_ns, us_n, gd_n, gc_n = cfg5_measure(g_nccl)
+            same = bool(torch.equal(gd_n.reshape(gd.shape), gd) and torch.equal(gc_n.reshape(gc.shape), gc))
+            assert same or gather.transport != "p2p", "peer-memory gather and NCCL all-gather returned different detections"
+            nccl_ctl = {"images_per_s": world * B5 * n5 / (ms_n / 1e3), "ms_per_step": ms_n / n5, "serialised_ms_per_step": ms_ns / n5,
+                        "allgather_us": us_n, "same_rows_as_p2p": same,
+                        "what": "the same flow with ONE all_gather_into_tensor over NCCL on a side stream (sharding.DetectionGather, round 1's "
+                                "transport), for comparison"}
         ms_det_only, _ = timed_loop(lambda k: (batched.detect(loc5, conf5, lm5, pr5, VAR, keep_topk=keep5,
                                                               out=(gather.dets(0), gather.counts(0), kidx5)),
                                                batched.correct_boxes(gather.dets(0), gather.counts(0), post5, letterbox=False,
                                                                      to_pixels=True)), n5)
         cfg5_info = {"images_per_s": world * B5 * n5 / (ms5 / 1e3), "ms_per_step": ms5 / n5,
                      "serialised_ms_per_step": ms5_serial / n5, "detect_only_ms_per_step": ms_det_only / n5,
-                     "allgather_us": us_ag, "allgather_overlapped": world > 1,
+                     "transport": gather.transport,
+                     "allgather_us": us_ag, "allgather_overlapped": True,
                      "allgather_exposed_us": max(ms5 - ms_det_only, 0.0) / n5 * 1e3,
                      "allgather_bytes_per_rank": int(gather.L * 4),
+                     "nccl_control": nccl_ctl,
                      "what": "per rank: fused detect of 32 x 640^2 images (score>0.02, top-5000, IoU 0.4, keep 750) + pixel scaling into "
-                             "the send buffer, then ONE all_gather_into_tensor of [32*750*15 floats | 32 counts] over %s on a side stream "
-                             "(sharding.DetectionGather, two slots): batch k+1 is detected while batch k is gathered; "
-                             "serialised_ms_per_step waits for each gather in line (round 1's flow)"
-                             % ("NCCL" if world > 1 else "a single rank (device copy)")}
+                             "the send buffer, then the exchange of [32*750*15 floats | 32 counts] on a side stream: transport 'p2p' = "
+                             "jabd_p2p_allgather, this library's kernel storing the block straight into every rank's receive buffer over "
+                             "NVLink (sharding.PeerGather, three slots, flags + acknowledgements in peer memory, no host sync); 'nccl' = "
+                             "all_gather_into_tensor (fallback when peers cannot be mapped).  Batch k+1 is detected while batch k is "
+                             "exchanged; serialised_ms_per_step waits for each exchange in line (round 1's flow)"}
         if rank == 0:
             gd2 = gd.reshape(world * B5, keep5, 15).contiguous()
             preds5 = utils_map.dets_to_pred_rows(gd2, gc.reshape(-1).contiguous())

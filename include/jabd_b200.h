@@ -297,6 +297,38 @@ JABD_API int jabd_detect_host_async(const float *loc_host, const float *conf_hos
                               float *dets_host, int *counts_host, int *keep_idx_host, void *dev_scratch,
                               size_t dev_scratch_bytes, jabd_stream_t stream);
 
+/* ---- peer-memory exchange of the validation flow over NVLink / NVSwitch (csrc/p2p.cu) ---------------------------------
+ * Replaces the reference's pickle -> pad -> two all_gather pattern for evaluation results (R/utils.py:62-90) and the NCCL
+ * all-gather of sharding.DetectionGather: every rank copies its block of padded detections straight into slot `rank` of every
+ * rank's receive buffer (16-byte peer stores, one NVSwitch hop) and raises a flag there; consumers wait on their own flags.
+ * One process per GPU: buffers are exported / imported as CUDA IPC handles, which the caller ships over its host channel.
+ * These four calls are the one place the library allocates device memory, explicitly and at the caller's request: IPC handles
+ * need an allocation of their own (a framework's caching allocator hands out interior pointers).  alloc zero-fills and
+ * synchronises the device once; open / close / free are the matching calls on the peers / the owner. */
+#define JABD_P2P_HANDLE_BYTES 64
+#define JABD_P2P_MAX_PEERS 16
+JABD_API int jabd_p2p_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64);
+JABD_API int jabd_p2p_open(const unsigned char *handle64, void **dev_ptr);
+JABD_API int jabd_p2p_close(void *dev_ptr);
+JABD_API int jabd_p2p_free(void *dev_ptr);
+/* ONE kernel: copies `bytes` from src (device, 16-byte aligned) to peer_bufs[j] + dst_offset for every j < n_ranks (HOST arrays
+ * of device pointers as mapped in THIS process; entry `rank` is the own buffer) and then stores `seq` into peer_flags[j][rank]
+ * with system-scope release.  counters: n_ranks zeroed unsigned ints in device memory, private to the stream (left zero again).
+ * seq must increase from one exchange to the next on the same flags.  bytes == 0 (src may be null) only raises the flags.
+ * Handshake, ack_seq != 0: before anything is stored into peer j's buffer the kernel (a) stores ack_seq into peer_acks[j][rank]
+ * -- "this rank has read what j sent into this slot last time"; the call must therefore be stream-ordered behind those reads --
+ * and (b) waits until own_acks[j] >= ack_seq, i.e. until j has said the same (time-out as in jabd_p2p_wait, *status = 101 + j). */
+JABD_API int jabd_p2p_allgather(const void *src, size_t bytes, void *const *peer_bufs, size_t dst_offset,
+                                unsigned long long *const *peer_flags, unsigned long long *const *peer_acks,
+                                const unsigned long long *own_acks, int n_ranks, int rank, unsigned long long seq,
+                                unsigned long long ack_seq, unsigned int *counters, double timeout_s, int *status,
+                                jabd_stream_t stream);
+/* Enqueues a one-CTA kernel that returns once flags[j] >= seq for every j < n_ranks (system-scope acquire): work enqueued after
+ * it on `stream` sees all n_ranks blocks.  After timeout_s (<= 0: 2 s) of spinning it gives up and stores 1 + j into *status
+ * (device int, may be null) instead of hanging the device. */
+JABD_API int jabd_p2p_wait(const unsigned long long *flags, int n_ranks, unsigned long long seq, double timeout_s, int *status,
+                           jabd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

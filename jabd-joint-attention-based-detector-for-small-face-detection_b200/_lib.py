@@ -73,6 +73,13 @@ SIGNATURES = {
                                  c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "jabd_detect_host_async": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64,
                                        c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_p2p_alloc": (c_int, [c_sz, c_vp, c_vp]),
+    "jabd_p2p_open": (c_int, [c_vp, c_vp]),
+    "jabd_p2p_close": (c_int, [c_vp]),
+    "jabd_p2p_free": (c_int, [c_vp]),
+    "jabd_p2p_allgather": (c_int, [c_vp, c_sz, c_vp, c_sz, c_vp, c_vp, c_vp, c_int, c_int, ctypes.c_uint64, ctypes.c_uint64, c_vp,
+                                   c_f64, c_vp, c_vp]),
+    "jabd_p2p_wait": (c_int, [c_vp, c_int, ctypes.c_uint64, c_f64, c_vp, c_vp]),
 }
 
 # libjabd_b200_selftest.so (include/jabd_b200_selftest.h): test / bench hooks, deliberately not in the product library
