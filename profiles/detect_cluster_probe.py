@@ -40,7 +40,7 @@ for (size, B, gen) in ((640, 32, "B"), (1024, 16, "B"), (1024, 16, "A"), (640, 1
     print("%dx%d B=%d gen %s kept %.0f: %s" % (size, size, B, gen, ref[1].float().mean().item(), "; ".join(line)), flush=True)
 
 # host-buffer pipeline depth (HostDetect.submit / wait): 640^2 x 32 and cfg3
-for (size, B) in ((640, 32), (1024, 16)):
+for (size, B) in (((640, 32), (1024, 16)) if "--host" in sys.argv else ()):
     pri = anchors.Anchors(config.cfg_mnet, image_size=(size, size)).get_anchors()
     P = pri.shape[0]
     ls, cs, ms = [], [], []

@@ -54,6 +54,12 @@ for (size, B, gen) in ((640, 32, "B"), (640, 1, "B"), (1024, 16, "B"), (1024, 16
             run()
             L.jabd_debug_detect_profile(prof, 1)
             ch = max(prof[15], 1)
+            if os.environ.get("JABD_PROBE_WINDOW", "1") == "1":
+                print("   mode %d width %s CTA0 cycles: select %d (histogram %d, compaction %d, sort %d + run exchange %d + rank merge %d), decode %d; "
+                      "%d windows (mean alive %d), per window (thread 0): kept-list tests %d, wait %d, exchange+compaction %d, triangle %d, wait %d, "
+                      "resolve %d" % (mode, width or "auto", prof[0], prof[5], prof[6], prof[2], prof[3], prof[4], prof[1], prof[15], prof[14] // ch,
+                                      prof[8] // ch, prof[9] // ch, prof[10] // ch, prof[11] // ch, prof[12] // ch, prof[13] // ch))
+                continue
             print("   mode %d width %s CTA0 cycles: select %d (histogram passes %d, compaction %d, sort %d + run exchange %d + rank merge %d), decode %d; %d chunks, per chunk: "
                   "query %d, wait for slowest warp %d, cluster exchange %d, resolve %d, wait for next triangle %d; warp 1: next triangle %d, look-ahead %d" %
                   (mode, width or "auto", prof[0], prof[5], prof[6], prof[2], prof[3], prof[4], prof[1], prof[15], prof[8] // ch, prof[9] // ch,

@@ -57,12 +57,13 @@ def test_library_is_sm100a_with_tma(lib):
     assert "UBLKCP" in sass and "SYNCS" in sass           # cp.async.bulk + mbarrier in the matching kernel
     assert "REDUX" in sass                                # warp argmax
     assert "UCGABAR_ARV" in sass and "UCGABAR_WAIT" in sass   # thread-block cluster barrier (loss forward, DSMEM histograms)
-    # the detect / NMS kernels are cluster kernels too: per-function check that the barrier and the flagged 8-byte
-    # distributed-shared-memory store of the mask exchange (st.relaxed.cluster -> ST.E.64.STRONG.GPU) are in their code
+    # the detect / NMS kernels are cluster kernels too: per-function check that the cluster barrier (arrive + wait) and generic
+    # stores to mapped distributed-shared-memory addresses (st.shared::cluster -> ST.E / ST.E.128: candidate boxes, window masks,
+    # triangle words of the NMS loop) are in their code
     for fn in ("detect_kernel", "nms_kernel"):
         body = sass.split("Function : ")
         mine = [b for b in body if b.split("\n", 1)[0].find(fn) >= 0]
-        assert mine and all("UCGABAR_ARV" in b and "ST.E.64.STRONG" in b for b in mine), fn
+        assert mine and all("UCGABAR_ARV" in b and "UCGABAR_WAIT" in b and "ST.E.128" in b and "ST.E " in b for b in mine), fn
 
 
 def test_host_side_validation_without_gpu(lib):
