@@ -9,7 +9,8 @@
  *   - Every pointer is DEVICE memory on the current CUDA device unless the name ends in `_host`.
  *   - fp32 data, C-contiguous.  `conf_t` is int64 (torch.LongTensor, R/nets/retinaface_training.py:199).
  *   - The caller owns every buffer, including the workspace; the library never allocates or frees
- *     device memory, keeps no pointer after return and has no global mutable state: every option is an
+ *     device memory (one explicit exception: jabd_p2p_alloc / jabd_p2p_free, IPC-exportable buffers of the
+ *     peer-memory exchange), keeps no pointer after return and has no global mutable state: every option is an
  *     argument of the call it affects.  (Process-wide memo tables of *device properties* -- shared-memory opt-in
  *     done, resident clusters per width -- are atomics and never depend on a call's arguments.)
  *   - Test and bench hooks (division self-test, FP32 probe) are NOT part of this ABI: they live in
