@@ -766,17 +766,20 @@ def main():
                 gather.launch(slot)
                 if not overlap:
                     gather.result(slot)     # serialised variant: the step's stream waits for its own exchange
-                elif k >= 1:
-                    gather.result((k - 1) % depth)
+                elif k >= lag:
+                    gather.result((k - lag) % depth)    # the consumer runs `lag` batches behind the producer
+            lag = 2 if depth >= 3 else 1    # three slots: two batches of slack absorb the ranks' step-to-step jitter
             for k in range(2 * depth):
                 step(k)
-            gather.result((2 * depth - 1) % depth)
+            for j in range(lag):
+                gather.result((2 * depth - 1 - j) % depth)
 
             def loop(overlap):
                 def body(k):
                     step(k, overlap)
-                    if k == n5 - 1:         # drain inside the timed region: the last exchange is part of the K steps
-                        gather.result(k % depth)
+                    if k == n5 - 1:         # drain inside the timed region: the last exchanges are part of the K steps
+                        for j in range(lag - 1, -1, -1):
+                            gather.result((k - j) % depth)
                 ms_, _ = timed_loop(body, n5)
                 return ms_
             ms_o = loop(True)
