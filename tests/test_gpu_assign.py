@@ -255,6 +255,53 @@ def test_assign_edge_cases(mods):
     assert np.array_equal(out[1][0].cpu().numpy(), ref["conf_t"][0]) and np.array_equal(out[1][2].cpu().numpy(), ref["conf_t"][1])
 
 
+def test_assign_encode_kernel_paths(mods):
+    """The pipelined encode kernel (256 priors x 8 images per CTA) off its main road: an odd prior count (rows of odd images
+    are only 8-byte aligned: scalar landmark stores), 11 images (a full group of 8 and a group of 3, an image without GT in
+    each), priors and GT rows that fail the once-per-prior / once-per-row range test (generic divide), every kernel variant
+    (landmarks on/off, encode on/off, extra outputs on/off)."""
+    orc = mods["orc"]
+    pri_full = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(160, 192)).get_anchors()
+    pn = pri_full.cpu().numpy()[:1261].copy()                 # odd P, last tile partial
+    pn[7] = [1e-13, 0.5, 0.1, 0.1]                            # |cx| < 2^-36: prior fails the range test
+    pn[300] = [0.5, 0.5, 1e-11, 0.2]                          # var0*w below 2^-36 (area still within the match kernel's bounds)
+    pri = torch.from_numpy(pn).cuda()
+    rng = np.random.default_rng(5)
+    targets = []
+    for i in range(11):
+        G = [3, 0, 40, 1, 70, 5, 2, 9, 0, 130, 4][i]
+        c = rng.random((G, 2), dtype=np.float32) * 0.8
+        wh = 0.02 + 0.2 * rng.random((G, 2), dtype=np.float32)
+        r = np.zeros((G, 15), np.float32)
+        r[:, :2], r[:, 2:4] = c, c + wh
+        r[:, 4:14] = rng.random((G, 10), dtype=np.float32)
+        r[:, 14] = np.where(rng.random(G) < 0.5, 1.0, -1.0)
+        if G >= 40:
+            r[1, 4] = 3e18                                    # a landmark beyond 2^59: the row fails the range test
+            r[2, 2] = r[2, 0]                                 # zero width: log(0) = -inf like the reference
+        targets.append(r)
+    nonempty = [t for t in targets if len(t)]
+    ref_all = orc.match_batch(THR, nonempty, pn, VAR)
+    b = mods["batched"]
+    for kw in (dict(), dict(return_match=True), dict(encode=False), dict(encode=False, return_match=True)):
+        out = b.assign_targets(pri, [cuda(t) for t in targets], threshold=THR, variances=VAR, allow_empty=True, **kw)
+        loc_t, conf_t, landm_t = out[0].cpu().numpy(), out[1].cpu().numpy(), out[2].cpu().numpy()
+        ref = ref_all if kw.get("encode", True) else orc.match_batch(THR, nonempty, pn, VAR, encode_mode=0)
+        j = 0
+        for i, t in enumerate(targets):
+            if len(t) == 0:
+                assert not conf_t[i].any() and not loc_t[i].any() and not landm_t[i].any(), i
+                continue
+            assert np.array_equal(conf_t[i], ref["conf_t"][j]), (i, kw)
+            with np.errstate(invalid="ignore"):
+                np.testing.assert_array_equal(landm_t[i], ref["landm_t"][j], err_msg=str((i, kw)))
+                np.testing.assert_array_equal(loc_t[i][:, :2], ref["loc_t"][j][:, :2], err_msg=str((i, kw)))
+                np.testing.assert_allclose(loc_t[i], ref["loc_t"][j], rtol=RTOL, atol=ATOL, err_msg=str((i, kw)))
+            if kw.get("return_match"):
+                assert np.array_equal(out[3]["best_truth_idx"][i].cpu().numpy(), ref["best_truth_idx"][j]), (i, kw)
+            j += 1
+
+
 def test_assign_cfg4_dense_tiny_faces(mods):
     """BASELINE configs[3]: 2048x2048 (172,032 priors), 1,500 GT per image (3 GT chunks per CTA)."""
     pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(2048, 2048)).get_anchors()
