@@ -29,6 +29,7 @@ VAR = (0.1, 0.2)
 THR = 0.35
 IMAGE = (640, 640)
 BATCH = 32            # images per GPU per step (cfg2; cfg5 = 256 over 8 GPUs)
+LANES = 4             # side streams the steps of one graph are dealt over (jabd_assign_batches): independent batches overlap
 SETS = 8              # rotating buffer sets: 8 x ~45 MB of outputs+workspace > 126 MB L2
 POOL = 256            # distinct images every N draws its global batches from (N = 8: one step = the whole pool = cfg5)
 METRIC = "images/s for prior match+encode and decode+NMS @640^2 (16.8k priors), 1-8 GPU"
@@ -323,7 +324,7 @@ def main():
             fn()
         return g
 
-    def step_graphs(ss):
+    def step_graphs(ss, lanes_n):
         """One graph per buffer set (a step = 3 kernel launches) and one graph holding a step of every set back to back: the
         timed loop replays the long one while >= SETS steps remain, so that the host's launch cadence (one cudaGraphLaunch
         per ~40 us step, from N processes on shared vCPUs) is not what is measured."""
@@ -331,10 +332,22 @@ def main():
             assign(s_)
         torch.cuda.synchronize(dev)
         singles = [capture(lambda s_=s_: assign(s_)) for s_ in ss]
-        chunk = capture(lambda: [assign(s_) for s_ in ss])
+        chunk = capture(lambda: assign_batches(ss, lanes_n))
         return singles, chunk
 
-    singles, chunk = step_graphs(sets)
+    def assign_batches(ss, n_lanes):
+        """jabd_assign_batches: the steps of ss (independent batches, own outputs and workspaces) on n_lanes side streams,
+        forked from and joined back into the current stream -- n_lanes = 0: back to back on the current stream."""
+        arr = (_lib.AssignBatch * len(ss))(*[
+            _lib.AssignBatch(s_["gt"].data_ptr(), s_["offs"].data_ptr(), s_["B"], s_["sumG"], s_["loc"].data_ptr(), s_["conf"].data_ptr(),
+                             s_["landm"].data_ptr(), s_["ws"].data_ptr(), s_["ws"].numel()) for s_ in ss])
+        ls = batched.lanes(dev, n_lanes)
+        la = (ctypes.c_void_p * max(len(ls), 1))(*[x.cuda_stream for x in ls])
+        _lib.call("jabd_assign_batches", ptr(pri), P, ctypes.cast(arr, ctypes.c_void_p), len(ss), THR, VAR[0], VAR[1], 0, 1, 0,
+                  ctypes.cast(la, ctypes.c_void_p), len(ls), cur_stream())
+
+    singles, chunk = step_graphs(sets, LANES)
+    _, serial_chunk = step_graphs(sets, 0)
 
     def run_steps(n, singles=singles, chunk=chunk):
         k = 0
@@ -392,7 +405,7 @@ def main():
             del full
             assert shard_check["equal"], "sharded result differs from the single-GPU result: %s" % (shard_check,)
         ctrl_sets = [make_set(list(range(s * BATCH, (s + 1) * BATCH))) for s in range(SETS)]
-        c_singles, c_chunk = step_graphs(ctrl_sets)
+        c_singles, c_chunk = step_graphs(ctrl_sets, LANES)
         run_steps(W, c_singles, c_chunk)
         ms_c, _ = timed_loop(lambda k: run_steps(K, c_singles, c_chunk) if k == 0 else None, 1)
         control = {"value": world * BATCH * K / (ms_c / 1e3), "unit": "images/s", "ms_per_step": ms_c / K,
@@ -421,6 +434,9 @@ def main():
     ms_match, _ = timed_loop(lambda k: g_pm.replay(), n_ph)
     ms_enc, _ = timed_loop(lambda k: g_enc.replay(), n_ph)
     us_prep, us_pm, us_enc = (x / (n_ph * SETS) * 1e3 for x in (ms_prep, ms_match, ms_enc))
+    serial_chunk.replay()
+    ms_serial, _ = timed_loop(lambda k: serial_chunk.replay(), n_ph)
+    us_serial = ms_serial / (n_ph * SETS) * 1e3               # the same steps back to back on one stream (rounds 1-2's number)
     us_match = max(us_pm - us_prep, 1e-3)
     hbm_peak, peak_src = peaks()
     sum_g = sum(s["sumG"] for s in sets) / SETS
@@ -464,12 +480,15 @@ def main():
                 "note": "achieved = 14 fp32 ops x P x sum(G) (dense-equivalent, SURVEY 8d) / kernel time; the kernel culls GT "
                         "against each warp's prior bounding box, so executed flops are lower than this (see phases.match_dense_*)",
                 "step": {"ms_per_step": ms / K, "bound_us": max(t_fp32_us, t_hbm_us), "frac": max(t_fp32_us, t_hbm_us) / (ms / K * 1e3),
-                         "note": "whole step (all launches) against max(t_FP32 dense-equivalent, t_HBM) of SURVEY 8(d)"}}
+                         "serial_us_per_step": us_serial, "serial_frac": max(t_fp32_us, t_hbm_us) / us_serial,
+                         "note": "whole step (all launches) against max(t_FP32 dense-equivalent, t_HBM) of SURVEY 8(d); ms_per_step: "
+                                 "independent batches dealt over %d side streams (jabd_assign_batches), serial_*: the same steps "
+                                 "back to back on one stream" % LANES}}
     roofline_encode = {"kernel": "match_encode_kernel", "bound": "hbm", "achieved": enc_gbs, "peak": hbm_peak, "unit": "GB/s",
                        "frac": enc_gbs / hbm_peak, "traffic": traffic.get("match_encode_kernel_bytes_per_launch"),
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_step, "launch_us": us_enc,
                        "note": "80*P + 60*G bytes per image (SURVEY 8d) x 32 images; loc/conf/landm targets written once"}
-    phases = {"prep_us": us_prep, "match_us": us_match, "match_encode_us": us_enc,
+    phases = {"prep_us": us_prep, "match_us": us_match, "match_encode_us": us_enc, "serial_step_us": us_serial, "lanes": LANES,
               "match_dense_equiv_tflops": match_tflops, "fp32_peak_measured_tops": fp32_peak, "fp32_peak_nominal_tops": fp32_nominal}
 
     extras = not args.no_extras
@@ -889,6 +908,11 @@ def main():
                    "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2); steps replayed from CUDA graphs "
                          "(one graph of %d steps while >= %d remain, single-step graphs for the rest)"
                          % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6, SETS, SETS),
+                   "overlap": "the %d steps of a graph are %d independent batches issued through ONE jabd_assign_batches call: batch i on "
+                              "side stream i %% %d, forked from and joined into the timing stream, so that one batch's staging and "
+                              "encode kernels run in the ramp and tail of another batch's persistent matching kernel; every step still "
+                              "launches its own 3 kernels on its own batch, outputs and workspace (roofline.step.serial_us_per_step: "
+                              "the same steps back to back on one stream)" % (SETS, SETS, LANES),
                    "cpu_affinity": None if my_cpus is None else {"rank0_cpus": len(my_cpus), "visible": len(all_cpus)}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode,
         "cpu_baseline": cpu, "phases": phases, "cfg1": cfg1_info, "cfg4": cfg4_info,

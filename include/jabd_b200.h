@@ -114,6 +114,28 @@ JABD_API int jabd_assign(const float *priors, int64_t P, const float *gt, const 
                          float *loc_t, int64_t *conf_t, float *landm_t, int *best_truth_idx, float *best_truth_overlap,
                          int *best_prior_idx, float *best_prior_overlap, void *workspace, size_t workspace_bytes,
                          jabd_stream_t stream);
+/* Several independent batches in one call (a data loader's prefetch queue, gradient-accumulation micro-batches: the
+ * reference calls MultiBoxLoss.forward once per batch, R/nets/retinaface_training.py:197-227, and nothing couples two
+ * batches).  Batch i is enqueued on lanes[i % n_lanes] -- caller-owned streams, distinct from `stream` and from each other --
+ * so that one batch's staging and encode kernels fill the SMs the persistent matching kernel of another leaves idle on its
+ * ramp and tail (cfg2: 27 us per batch instead of 33).  Every lane is ordered after `stream` at entry and `stream` after
+ * every lane at exit (events; nothing synchronises the host), so to the caller this behaves like n_batches jabd_assign calls
+ * on `stream`; it may be captured into a CUDA graph through `stream`.  n_lanes == 0: the batches run back to back on
+ * `stream`.  Every batch needs its own outputs and its own workspace; `priors` and the scalar options are shared. */
+typedef struct {
+    const float *gt;      /* [sumG,15] */
+    const int *gt_off;    /* [B+1] */
+    int B;
+    int64_t sumG;
+    float *loc_t;         /* [B,P,4] */
+    int64_t *conf_t;      /* [B,P] */
+    float *landm_t;       /* [B,P,10] or NULL */
+    void *workspace;      /* jabd_assign_workspace_bytes(B, P, sumG) */
+    size_t workspace_bytes;
+} jabd_assign_batch_t;
+JABD_API int jabd_assign_batches(const float *priors, int64_t P, const jabd_assign_batch_t *batches_host, int n_batches,
+                                 float threshold, float var0, float var1, int label_mode, int encode_mode, int flags,
+                                 const jabd_stream_t *lanes_host, int n_lanes, jabd_stream_t stream);
 /* The two phases of jabd_assign, exposed for per-kernel timing (bench.py roofline) and tests:
  * _match  = GT staging + IoU + both argmaxes into the workspace; _encode = force-match + gather + encode. */
 JABD_API int jabd_assign_match(const float *priors, int64_t P, const float *gt, const int *gt_off, int B, int64_t sumG,

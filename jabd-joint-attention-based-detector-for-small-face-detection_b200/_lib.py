@@ -16,6 +16,12 @@ CSRC = os.path.join(_HERE, "csrc")
 c_int, c_i64, c_f32, c_f64, c_sz, c_vp = (ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double,
                                           ctypes.c_size_t, ctypes.c_void_p)
 
+class AssignBatch(ctypes.Structure):
+    """``jabd_assign_batch_t`` of include/jabd_b200.h (one batch of ``jabd_assign_batches``)."""
+    _fields_ = [("gt", c_vp), ("gt_off", c_vp), ("B", c_int), ("sumG", c_i64), ("loc_t", c_vp), ("conf_t", c_vp),
+                ("landm_t", c_vp), ("workspace", c_vp), ("workspace_bytes", c_sz)]
+
+
 # name -> (restype, argtypes); mirrors include/jabd_b200.h one to one
 SIGNATURES = {
     "jabd_version": (c_int, []),
@@ -33,6 +39,7 @@ SIGNATURES = {
     "jabd_assign_workspace_bytes": (c_sz, [c_int, c_i64, c_i64]),
     "jabd_assign": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_assign_batches": (c_int, [c_vp, c_i64, c_vp, c_int, c_f32, c_f32, c_f32, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "jabd_assign_match": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_sz, c_vp]),
     "jabd_assign_encode": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int,
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

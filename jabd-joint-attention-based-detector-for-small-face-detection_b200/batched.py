@@ -17,7 +17,7 @@ import torch
 from . import _lib, _tensor
 from ._tensor import ptr
 
-__all__ = ["assign_targets", "detect", "pack_targets", "assign_targets_host", "detect_host", "multibox_loss", "correct_boxes", "letterbox_params"]
+__all__ = ["assign_targets", "assign_batches", "AssignBatches", "detect", "pack_targets", "assign_targets_host", "detect_host", "multibox_loss", "correct_boxes", "letterbox_params"]
 
 THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
 FLAG_DENSE = 1
@@ -107,6 +107,77 @@ def assign_targets(priors, targets, threshold=0.35, variances=(0.1, 0.2), label_
     if return_match:
         return loc_t, conf_t, landm_t, extra
     return loc_t, conf_t, landm_t
+
+
+_LANES = {}
+
+
+def lanes(device, n):
+    """``n`` side streams of ``device`` for ``assign_batches`` (created once per device, reused by every call)."""
+    have = _LANES.setdefault(torch.device(device), [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(device))
+    return have[:n]
+
+
+class AssignBatches(object):
+    """Target assignment of several independent batches per call (``jabd_assign_batches``): batch i runs on side stream
+    ``i % lanes``, so that one batch's staging and encode kernels fill the SMs another batch's persistent matching kernel
+    leaves idle on its ramp and tail; the caller's stream is ordered before and after all of them (no host
+    synchronisation, capturable into a CUDA graph).  The reference has one ``MultiBoxLoss.forward`` call per batch
+    (R/nets/retinaface_training.py:197-227) and nothing couples two batches -- a prefetching data loader or
+    gradient-accumulation micro-batches give several at once.
+
+    ``plan = AssignBatches(priors, [targets_0, targets_1, ...])`` packs the GT and owns outputs and workspaces;
+    ``plan()`` enqueues everything and returns ``[(loc_t, conf_t, landm_t), ...]`` (the same tensors on every call).
+    """
+
+    def __init__(self, priors, batches, threshold=0.35, variances=(0.1, 0.2), label_mode=0, encode=True, dense=False,
+                 with_landm=True, lanes_n=4, device=None):
+        first = batches[0] if len(batches) else None
+        dev = device or _tensor.device_of(priors, first[0] if isinstance(first, (list, tuple)) and len(first) else None)
+        self.dev = torch.device(dev)
+        self.pri = _tensor.to_dev(priors, self.dev)
+        if self.pri.ndim != 2 or self.pri.shape[1] != 4:
+            raise ValueError("priors must be [P, 4]")
+        self.P = int(self.pri.shape[0])
+        self.opts = (float(threshold),) + _tensor.variances_of(variances) + (int(label_mode), 1 if encode else 0,
+                                                                             FLAG_DENSE if dense else 0)
+        L = _lib.lib()
+        self.items, self.outputs = [], []
+        arr = (_lib.AssignBatch * max(len(batches), 1))()
+        for i, tg in enumerate(batches):
+            gt, offs, offs_host = pack_targets(tg, self.dev)
+            B, sumG = len(offs_host) - 1, int(gt.shape[0])
+            if any(b == a for a, b in zip(offs_host, offs_host[1:])):
+                raise ValueError("AssignBatches: an image of batch %d has no ground truth" % i)
+            ws = _tensor.workspace(L.jabd_assign_workspace_bytes(B, self.P, sumG), self.dev)
+            loc_t = torch.empty((B, self.P, 4), dtype=torch.float32, device=self.dev)
+            conf_t = torch.empty((B, self.P), dtype=torch.int64, device=self.dev)
+            landm_t = torch.empty((B, self.P, 10), dtype=torch.float32, device=self.dev) if with_landm else None
+            self.items.append((gt, offs, ws))
+            self.outputs.append((loc_t, conf_t, landm_t))
+            arr[i] = _lib.AssignBatch(gt.data_ptr() or None, offs.data_ptr(), B, sumG, loc_t.data_ptr(), conf_t.data_ptr(),
+                                      landm_t.data_ptr() if with_landm else None, ws.data_ptr(), ws.numel())
+        self.n = len(batches)
+        self.arr = arr
+        self.set_lanes(lanes_n)
+
+    def set_lanes(self, lanes_n):
+        self.lane_streams = lanes(self.dev, max(0, min(int(lanes_n), self.n)))
+        self.lane_arr = (ctypes.c_void_p * max(len(self.lane_streams), 1))(*[s.cuda_stream for s in self.lane_streams])
+
+    def __call__(self):
+        t, v0, v1, lm, enc, fl = self.opts
+        with torch.cuda.device(self.dev):
+            _lib.call("jabd_assign_batches", ptr(self.pri), self.P, ctypes.cast(self.arr, ctypes.c_void_p), self.n, t, v0, v1, lm,
+                      enc, fl, ctypes.cast(self.lane_arr, ctypes.c_void_p), len(self.lane_streams), _tensor.stream_of(self.dev))
+        return self.outputs
+
+
+def assign_batches(priors, batches, **kw):
+    """One-shot form of ``AssignBatches``: ``[(loc_t, conf_t, landm_t), ...]`` for a list of batches."""
+    return AssignBatches(priors, batches, **kw)()
 
 
 def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000,

@@ -856,6 +856,60 @@ int jabd_assign(const float *priors, int64_t P, const float *gt, const int *gt_o
                               workspace_bytes, stream);
 }
 
+int jabd_assign_batches(const float *priors, int64_t P, const jabd_assign_batch_t *batches, int n_batches, float threshold,
+                        float var0, float var1, int label_mode, int encode_mode, int flags, const jabd_stream_t *lanes,
+                        int n_lanes, jabd_stream_t stream)
+{
+    JABD_REQUIRE(n_batches >= 0 && (n_batches == 0 || batches), JABD_EINVAL, "assign_batches: null batch list or negative count");
+    JABD_REQUIRE(n_lanes >= 0 && n_lanes <= 64 && (n_lanes == 0 || lanes), JABD_EINVAL, "assign_batches: 0..64 lanes, non-null list");
+    for (int l = 0; l < n_lanes; ++l) {
+        JABD_REQUIRE(lanes[l] != stream, JABD_EINVAL, "assign_batches: lane %d is the calling stream", l);
+        for (int m = 0; m < l; ++m) JABD_REQUIRE(lanes[l] != lanes[m], JABD_EINVAL, "assign_batches: lanes %d and %d are the same stream", m, l);
+    }
+    // everything that can be refused is refused before the first lane is forked
+    for (int i = 0; i < n_batches; ++i) {
+        const jabd_assign_batch_t &b = batches[i];
+        int rc = check_assign_common(priors, P, b.gt, b.gt_off, b.B, b.sumG, b.workspace, b.workspace_bytes);
+        if (rc != JABD_OK) return rc;
+        if (b.B == 0 || P == 0) continue;
+        JABD_REQUIRE(b.loc_t && b.conf_t, JABD_EINVAL, "assign_batches: batch %d: loc_t/conf_t must not be null", i);
+        JABD_REQUIRE(aligned_to(b.loc_t, 16) && aligned_to(b.conf_t, 8) && aligned_to(b.landm_t, 4), JABD_EALIGN,
+                     "assign_batches: batch %d: loc_t needs 16-byte, conf_t 8-byte, landm_t 4-byte alignment", i);
+        for (int j = 0; j < i; ++j)
+            JABD_REQUIRE(batches[j].workspace != b.workspace || batches[j].B == 0, JABD_EINVAL,
+                         "assign_batches: batches %d and %d share a workspace", j, i);
+    }
+    const int used = n_lanes < n_batches ? n_lanes : n_batches;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaEvent_t fork = nullptr;
+    if (used > 0) {
+        JABD_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(fork, st);
+        for (int l = 0; l < used && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(static_cast<cudaStream_t>(lanes[l]), fork, 0);
+        cudaEventDestroy(fork);
+        if (e != cudaSuccess) return cuda_fail(e, "assign_batches: fork");
+    }
+    int rc = JABD_OK;
+    for (int i = 0; i < n_batches && rc == JABD_OK; ++i) {
+        const jabd_assign_batch_t &b = batches[i];
+        rc = jabd_assign(priors, P, b.gt, b.gt_off, b.B, b.sumG, threshold, var0, var1, label_mode, encode_mode, flags, b.loc_t,
+                         b.conf_t, b.landm_t, nullptr, nullptr, nullptr, nullptr, b.workspace, b.workspace_bytes,
+                         used > 0 ? lanes[i % used] : stream);
+    }
+    // join even after a failed launch: a lane forked into a stream capture must come back to it
+    for (int l = 0; l < used; ++l) {
+        cudaEvent_t join = nullptr;
+        cudaError_t e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+        if (e == cudaSuccess) {
+            e = cudaEventRecord(join, static_cast<cudaStream_t>(lanes[l]));
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
+            cudaEventDestroy(join);
+        }
+        if (e != cudaSuccess && rc == JABD_OK) rc = cuda_fail(e, "assign_batches: join");
+    }
+    return rc;
+}
+
 int64_t jabd_pack_gt_rows(const float *const *rows, const int *counts, int B, float *gt_packed, int64_t capacity_rows, int *gt_off)
 {
     JABD_REQUIRE(B >= 0 && gt_off && (B == 0 || (rows && counts)), JABD_EINVAL, "pack_gt_rows: null pointer or negative B");

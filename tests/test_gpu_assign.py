@@ -368,6 +368,65 @@ def test_assign_host_entry(mods):
     assert torch.equal(b[1], dev[1].flip(0)) and torch.equal(b[0], dev[0].flip(0))
 
 
+def test_assign_batches_lanes(mods):
+    """jabd_assign_batches: several independent batches on side streams (0, 1, 3, 4 lanes; eagerly and replayed from a CUDA
+    graph captured through the caller's stream) give, batch by batch, the bytes of one jabd_assign call each; the first batch
+    is also checked against the oracle."""
+    import ctypes
+    from jabd_b200 import _lib
+    bt = mods["batched"]
+    pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(640, 640)).get_anchors()
+    sizes = (5, 3, 8, 1, 6)
+    batches, first = [], 0
+    for n in sizes:
+        batches.append([t.cuda() for t in mods["synth"].make_gt_batch(2, n, (640, 640), first_image=first)])
+        first += n
+    want = [bt.assign_targets(pri, b, threshold=THR, variances=VAR) for b in batches]
+    ref = mods["orc"].match_batch(THR, [t.cpu().numpy() for t in batches[0]], pri.cpu().numpy(), VAR)
+    check_assign(want[0], None, ref)
+
+    def same(outs):
+        torch.cuda.synchronize()
+        return all(torch.equal(a, b) for o, w in zip(outs, want) for a, b in zip(o, w))
+
+    def scrub(outs):
+        for o in outs:
+            for t in o:
+                t.fill_(7)
+
+    for n_lanes in (0, 1, 3, 4, 9):
+        plan = bt.AssignBatches(pri, batches, threshold=THR, variances=VAR, lanes_n=n_lanes)
+        assert len(plan.lane_streams) == min(n_lanes, len(sizes))
+        outs = plan()
+        assert same(outs), n_lanes
+        scrub(outs)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):                       # a non-default calling stream; later work on it sees the results
+            outs = plan()
+            sums = [o[1].sum() for o in outs]
+        s.synchronize()
+        assert [int(x) for x in sums] == [int(w[1].sum()) for w in want]
+        assert same(outs)
+        scrub(outs)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            plan()
+        scrub(outs)
+        g.replay()
+        assert same(outs), ("graph", n_lanes)
+    assert same(bt.assign_batches(pri, batches[:2], threshold=THR, variances=VAR, lanes_n=2))
+    # refused before anything is enqueued: a lane equal to the calling stream, two batches on one workspace
+    plan = bt.AssignBatches(pri, batches[:2], lanes_n=1)
+    L = _lib.lib()
+    cur = torch.cuda.current_stream().cuda_stream
+    lane = (ctypes.c_void_p * 1)(cur)
+    args = (pri.data_ptr(), plan.P, ctypes.cast(plan.arr, ctypes.c_void_p), 2, THR, 0.1, 0.2, 0, 1, 0)
+    assert L.jabd_assign_batches(*args, ctypes.cast(lane, ctypes.c_void_p), 1, ctypes.c_void_p(cur)) == -1
+    assert "calling stream" in _lib.last_error()
+    plan.arr[1].workspace = plan.arr[0].workspace
+    assert L.jabd_assign_batches(*args, None, 0, ctypes.c_void_p(cur)) == -1 and "share a workspace" in _lib.last_error()
+
+
 def test_errors_are_loud(mods):
     from jabd_b200 import _lib
     pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(96, 128)).get_anchors()
