@@ -255,10 +255,10 @@ JABD_API int jabd_wider_eval(const double *pred, const int *pred_off, const doub
  *               than 2^-20 (relative) away from the threshold is decided by comparing inter with thr*union,
  *               which provably gives the same decision (detect.cu, suppresses()); tests compare the two. */
 #define JABD_NMS_EXACT_DIV 256
-/* jabd_nms / jabd_diounms / jabd_detect run each image (segment) on a thread-block cluster of 1, 2, 4 or 8 CTAs -- one SM
+/* jabd_nms / jabd_diounms / jabd_detect run each image (segment) on a thread-block cluster of 1 to 8 CTAs -- one SM
  * each -- picked per call as the widest cluster for which the whole batch is still co-resident.  A call may pin the width
  * (tests, measurements; results do not depend on it): `| JABD_NMS_CLUSTER(c)` in nms_mode, `JABD_DET_CLUSTER(c)` in the
- * flags of jabd_detect*; c = 0 (automatic, the default), 1, 2, 4 or 8. */
+ * flags of jabd_detect*; c = 0 (automatic, the default) or 1..8 (any count, not only powers of two). */
 #define JABD_NMS_CLUSTER(c) ((c) << 12)
 #define JABD_DET_CLUSTER(c) (c)
 /* Every jabd_nms / jabd_diounms / jabd_detect call leaves JABD_SEL_STATS ints per segment in its workspace at byte offset

@@ -22,7 +22,7 @@ for (size, B, gen) in ((640, 32, "B"), (1024, 16, "B"), (1024, 16, "A"), (640, 1
         ls.append(l.cuda()); cs.append(c.cuda()); ms.append(m.cuda())
     loc, conf, landm = torch.stack(ls).contiguous(), torch.stack(cs).contiguous(), torch.stack(ms).contiguous()
     ref, line = None, []
-    for width in (1, 2, 4, 8, 0):
+    for width in (1, 2, 3, 4, 5, 6, 7, 8, 0):
         for _ in range(3):
             out = batched.detect(loc, conf, landm, pri, VAR, cluster=width)
         torch.cuda.synchronize()

@@ -117,7 +117,7 @@ def fuzz_nms_tie_block(rng, trial):
     ref = orc.nms_tv(b, s, thr)
     cb, cs = cuda(b), cuda(s)
     exact = 0
-    for width in (1, 2, 4, 8, 0):
+    for width in (1, 2, 3, 4, 5, 6, 7, 8, 0):
         for cap in (n, 750):
             keep, cnt, st = _ops.nms_indices(cb, 4, cs, 1, n, 0.0, _ops.THRESH_NONE, 0, thr, _ops.NMS_TV, cap, dev, cluster=width,
                                              return_stats=True)

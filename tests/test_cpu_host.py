@@ -92,10 +92,10 @@ def test_host_side_validation_without_gpu(lib):
     mis = vp(buf.ctypes.data + 4)
     assert L.jabd_decode(mis, mis, 4, 1, 0.1, 0.2, mis, None) == -2
     assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 7, 0, 0.3, 0, 4, mis, mis, None, 0, None) == -1
-    # CTAs per image of the detect / NMS kernels: a per-call option (0 automatic, 1, 2, 4, 8), validated before any device call
-    assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 0, 0, 0.3, 3 << 12, 4, mis, mis, None, 0, None) == -1
+    # CTAs per image of the detect / NMS kernels: a per-call option (0 automatic, 1..8), validated before any device call
+    assert L.jabd_nms(mis, 0, 4, mis, 0, 1, 1, 4, 0.0, 0, 0, 0.3, 9 << 12, 4, mis, mis, None, 0, None) == -1
     assert "CTAs per segment" in lib.last_error()
-    assert L.jabd_detect(None, None, None, None, 1, 4, 0.1, 0.2, 0.02, 2, 0, 0.4, 4, 3, None, None, None, None, 0, None) == -1
+    assert L.jabd_detect(None, None, None, None, 1, 4, 0.1, 0.2, 0.02, 2, 0, 0.4, 4, 9, None, None, None, None, 0, None) == -1
     assert "CTAs per image" in lib.last_error()
     assert L.jabd_nms_stats_offset(2, 750) == 24064 + 6144 and L.jabd_nms_workspace_bytes(2, 100, 750) == 24064 + 6144 + 256
     offs = (ctypes.c_size_t * 4)()

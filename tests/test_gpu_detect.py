@@ -378,7 +378,7 @@ def test_nms_division_free_decision_equals_exact_and_oracle(mods, n):
 
 
 def test_detect_cluster_widths_agree(mods):
-    """One image on a thread-block cluster of 1, 2, 4 or 8 CTAs (split decode + kept-list slices, masks exchanged through
+    """One image on a thread-block cluster of 1..8 CTAs (split decode + kept-list slices, masks exchanged through
     distributed shared memory): keep lists, counts and rows are identical for every width and equal the oracle's; covers
     several images per launch, a ragged last chunk, an empty image and the landmark-less output stage."""
     orc, synth = mods["orc"], mods["synth"]
@@ -394,9 +394,9 @@ def test_detect_cluster_widths_agree(mods):
     conf[3, :, 1] = 0.0                                          # nothing above the threshold in image 3
     conf[3, :, 0] = 1.0
     with pytest.raises(ValueError):
-        mods["batched"].detect(loc, conf, landm, pri, VAR, cluster=3)
+        mods["batched"].detect(loc, conf, landm, pri, VAR, cluster=9)
     ref = None
-    for width in (1, 2, 4, 8, 0):
+    for width in (1, 2, 3, 4, 5, 6, 7, 8, 0):
         out = [mods["batched"].detect(loc, conf, landm, pri, VAR, cluster=width),                    # cfg3 parameters
                mods["batched"].detect(loc, conf, None, pri, VAR, conf_thres=0.3, strict=False, pre_nms_topk=1234,
                                       nms_thres=0.3, keep_topk=97, cluster=width)]
@@ -417,7 +417,7 @@ def test_detect_cluster_widths_agree(mods):
                 assert torch.equal(c, rc_) and torch.equal(k, rk) and torch.equal(d, rd), width
 
 
-@pytest.mark.parametrize("width", [2, 8])
+@pytest.mark.parametrize("width", [2, 5, 8])
 def test_nms_cluster_multi_round_and_workspace_spill(mods, width):
     """jabd_nms on a cluster: more candidates than one selection round (several decode exchanges) and more keeps than the
     shared-memory kept cache (slices read back from the workspace copy each CTA writes itself); SSD-legacy order too."""
@@ -442,7 +442,7 @@ def test_nms_cluster_multi_round_and_workspace_spill(mods, width):
 
 
 # ---------------------------------------------------------------------- exact three-pass select on a cluster (tie blocks)
-@pytest.mark.parametrize("width", [1, 2, 4, 8, 0])
+@pytest.mark.parametrize("width", [1, 2, 3, 4, 5, 6, 7, 8, 0])
 def test_nms_tie_block_exact_select_on_cluster(mods, width):
     """More than 8192 equal scores around the selection cut: the fine first histogram cannot isolate a small cut bin, so the
     exact three-pass radix select + ordered compaction run (first histogram shared by the cluster, passes 2-3 and the
@@ -480,7 +480,7 @@ def test_nms_tie_block_exact_select_on_cluster(mods, width):
     assert int(cnt.item()) == rc and np.array_equal(keep[:rc].cpu().numpy(), rk[:rc]) and int(st[1]) >= 1, width
 
 
-@pytest.mark.parametrize("width", [1, 2, 4, 0])
+@pytest.mark.parametrize("width", [1, 2, 3, 4, 6, 0])
 def test_detect_saturated_scores_on_cluster(mods, width):
     """An untrained network that scores every prior the same (and one that saturates half of them at 1.0): the fused kernel
     reaches the exact select at its default launch shape; candidates are then the lowest prior indices, like a stable sort."""
