@@ -51,14 +51,14 @@ torch.cuda.synchronize()
 ref = [(s["loc"].clone(), s["conf"].clone(), s["landm"].clone()) for s in sets]
 
 
-def graph(nstreams):
+def graph(nstreams, rounds=1):
     side = [torch.cuda.Stream(dev) for _ in range(nstreams - 1)]
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         cur = torch.cuda.current_stream(dev)
         for x in side:
             x.wait_stream(cur)
-        for i, s in enumerate(sets):
+        for i, s in enumerate(sets * rounds):      # set s always lands on lane s % nstreams: its reuse is stream-ordered
             k = i % nstreams
             if k == 0:
                 assign(s)
@@ -70,19 +70,22 @@ def graph(nstreams):
     return g
 
 
-for ns in (1, 2, 3, 4, 8):
-    g = graph(ns)
+for ns, rounds in ((1, 1), (2, 1), (3, 1), (4, 1), (8, 1), (4, 2), (4, 4), (4, 8), (2, 4), (8, 4)):
+    if SETS % ns and rounds > 1:
+        continue
+    g = graph(ns, rounds)
     for _ in range(20):
         g.replay()
     torch.cuda.synchronize()
-    reps = 250
+    reps = max(250 // rounds, 20)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
         g.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / (reps * SETS)
+    us = e0.elapsed_time(e1) * 1e3 / (reps * SETS * rounds)
     ok = all(torch.equal(a, s["loc"]) and torch.equal(b, s["conf"]) and torch.equal(c, s["landm"])
              for (a, b, c), s in zip(ref, sets))
-    print("streams %d: %.2f us per step  (%.0f img/s)  outputs equal: %s" % (ns, us, BATCH / us * 1e6, ok), flush=True)
+    print("streams %d, %d steps per graph: %.2f us per step  (%.0f img/s)  outputs equal: %s"
+          % (ns, SETS * rounds, us, BATCH / us * 1e6, ok), flush=True)
