@@ -30,6 +30,7 @@ THR = 0.35
 IMAGE = (640, 640)
 BATCH = 32            # images per GPU per step (cfg2; cfg5 = 256 over 8 GPUs)
 LANES = 4             # side streams the steps of one graph are dealt over (jabd_assign_batches): independent batches overlap
+ROUNDS = 4            # a lanes graph holds ROUNDS x SETS steps (the lanes drain at every graph boundary)
 SETS = 8              # rotating buffer sets: 8 x ~45 MB of outputs+workspace > 126 MB L2
 POOL = 256            # distinct images every N draws its global batches from (N = 8: one step = the whole pool = cfg5)
 METRIC = "images/s for prior match+encode and decode+NMS @640^2 (16.8k priors), 1-8 GPU"
@@ -332,7 +333,7 @@ def main():
             assign(s_)
         torch.cuda.synchronize(dev)
         singles = [capture(lambda s_=s_: assign(s_)) for s_ in ss]
-        chunk = capture(lambda: assign_batches(ss, lanes_n))
+        chunk = capture(lambda: assign_batches(ss * (ROUNDS if lanes_n else 1), lanes_n))   # set s always lands on lane s % LANES
         return singles, chunk
 
     def assign_batches(ss, n_lanes):
@@ -351,9 +352,9 @@ def main():
 
     def run_steps(n, singles=singles, chunk=chunk):
         k = 0
-        while n - k >= SETS:
+        while n - k >= SETS * ROUNDS:
             chunk.replay()
-            k += SETS
+            k += SETS * ROUNDS
         while k < n:
             singles[k % SETS].replay()
             k += 1
@@ -438,6 +439,39 @@ def main():
     ms_serial, _ = timed_loop(lambda k: serial_chunk.replay(), n_ph)
     us_serial = ms_serial / (n_ph * SETS) * 1e3               # the same steps back to back on one stream (rounds 1-2's number)
     us_match = max(us_pm - us_prep, 1e-3)
+
+    # the matching kernel as the lanes run it (work list of 192-GT items, launches of different batches overlapping):
+    # (prep + match) - (prep alone), both dealt over the lanes like the steps; and the same shape alone on one stream
+    TUNE_LANES = (192 << 8) | (192 << 16) | (100 << 24)          # JABD_ASSIGN_TUNE(192, 192, 100): what jabd_assign_batches picks
+
+    def lanes_graph(fn):
+        side = batched.lanes(dev, LANES)
+        for s_ in sets:
+            fn(s_)
+        torch.cuda.synchronize(dev)
+
+        def body():
+            cur = torch.cuda.current_stream(dev)
+            for x in side:
+                x.wait_stream(cur)
+            for i, s_ in enumerate(sets * ROUNDS):
+                with torch.cuda.stream(side[i % LANES]):
+                    fn(s_)
+            for x in side:
+                cur.wait_stream(x)
+        return capture(body)
+
+    n_pl = max(n_ph // ROUNDS, 10)
+    g_prep_l = lanes_graph(lambda s_: phase_match(s_, 2 | TUNE_LANES))
+    g_pm_l = lanes_graph(lambda s_: phase_match(s_, TUNE_LANES))
+    g_pm_a = phase_graph(lambda s_: phase_match(s_, TUNE_LANES))
+    for g in (g_prep_l, g_pm_l, g_pm_a):
+        g.replay()
+    ms_prep_l, _ = timed_loop(lambda k: g_prep_l.replay(), n_pl)
+    ms_pm_l, _ = timed_loop(lambda k: g_pm_l.replay(), n_pl)
+    ms_pm_a, _ = timed_loop(lambda k: g_pm_a.replay(), n_ph)
+    us_match_lanes = max((ms_pm_l - ms_prep_l) / (n_pl * SETS * ROUNDS) * 1e3, 1e-3)
+    us_match_lanes_shape_alone = max(ms_pm_a / (n_ph * SETS) * 1e3 - us_prep, 1e-3)
     hbm_peak, peak_src = peaks()
     sum_g = sum(s["sumG"] for s in sets) / SETS
     pairs = float(P) * sum_g                                   # prior x GT pairs per launch
@@ -478,7 +512,16 @@ def main():
                 "algorithmic_flops_per_launch": flops_launch, "launch_us": us_match,
                 "launch_us_how": "CUDA events around graphs of %d launches: (prep+match) - (prep alone), %d replays each" % (SETS, n_ph),
                 "note": "achieved = 14 fp32 ops x P x sum(G) (dense-equivalent, SURVEY 8d) / kernel time; the kernel culls GT "
-                        "against each warp's prior bounding box, so executed flops are lower than this (see phases.match_dense_*)",
+                        "against each warp's prior bounding box, so executed flops are lower than this (see phases.match_dense_*). "
+                        "launch_us is the kernel of a call that runs alone (work list of 64-GT items: short tail); the lanes of the "
+                        "timed step run it with 192-GT items (fewer items, less per-item work, a longer tail that the neighbouring "
+                        "launches fill): see `lanes`",
+                "lanes": {"work_list": "JABD_ASSIGN_TUNE(192, 192, 100)", "launch_us_overlapped": us_match_lanes,
+                          "frac_overlapped": flops_launch / (us_match_lanes * 1e-6) / 1e12 / fp32_peak,
+                          "launch_us_alone": us_match_lanes_shape_alone,
+                          "frac_alone": flops_launch / (us_match_lanes_shape_alone * 1e-6) / 1e12 / fp32_peak,
+                          "how": "overlapped: (prep+match) - (prep alone), both dealt over %d lanes in graphs of %d launches; alone: the "
+                                 "same shape back to back on one stream" % (LANES, SETS * ROUNDS)},
                 "step": {"ms_per_step": ms / K, "bound_us": max(t_fp32_us, t_hbm_us), "frac": max(t_fp32_us, t_hbm_us) / (ms / K * 1e3),
                          "serial_us_per_step": us_serial, "serial_frac": max(t_fp32_us, t_hbm_us) / us_serial,
                          "note": "whole step (all launches) against max(t_FP32 dense-equivalent, t_HBM) of SURVEY 8(d); ms_per_step: "
@@ -489,6 +532,7 @@ def main():
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_step, "launch_us": us_enc,
                        "note": "80*P + 60*G bytes per image (SURVEY 8d) x 32 images; loc/conf/landm targets written once"}
     phases = {"prep_us": us_prep, "match_us": us_match, "match_encode_us": us_enc, "serial_step_us": us_serial, "lanes": LANES,
+              "match_lanes_us": us_match_lanes, "match_lanes_shape_alone_us": us_match_lanes_shape_alone,
               "match_dense_equiv_tflops": match_tflops, "fp32_peak_measured_tops": fp32_peak, "fp32_peak_nominal_tops": fp32_nominal}
 
     extras = not args.no_extras
@@ -907,12 +951,12 @@ def main():
                                   "the same pool at every N) are cut into LPT shards of equal estimated cost" % (world, world * BATCH, POOL),
                    "l2": "%d rotating buffer sets per rank (%.0f MB of targets+workspace > 126 MB L2); steps replayed from CUDA graphs "
                          "(one graph of %d steps while >= %d remain, single-step graphs for the rest)"
-                         % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6, SETS, SETS),
-                   "overlap": "the %d steps of a graph are %d independent batches issued through ONE jabd_assign_batches call: batch i on "
+                         % (SETS, SETS * (BATCH * P * 72 + BATCH * P * 8) / 1e6, SETS * ROUNDS, SETS * ROUNDS),
+                   "overlap": "the %d steps of a graph are %d batches (independent: own GT, outputs, workspace) issued through ONE jabd_assign_batches call: batch i on "
                               "side stream i %% %d, forked from and joined into the timing stream, so that one batch's staging and "
                               "encode kernels run in the ramp and tail of another batch's persistent matching kernel; every step still "
                               "launches its own 3 kernels on its own batch, outputs and workspace (roofline.step.serial_us_per_step: "
-                              "the same steps back to back on one stream)" % (SETS, SETS, LANES),
+                              "the same steps back to back on one stream)" % (SETS * ROUNDS, SETS * ROUNDS, LANES),
                    "cpu_affinity": None if my_cpus is None else {"rank0_cpus": len(my_cpus), "visible": len(all_cpus)}},
         "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * K, "roofline": roofline, "roofline_encode": roofline_encode,
         "cpu_baseline": cpu, "phases": phases, "cfg1": cfg1_info, "cfg4": cfg4_info,

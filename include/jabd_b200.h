@@ -66,6 +66,13 @@ enum {
                                      HBM for the loss (what MultiBoxLoss.forward does with them, R/nets/retinaface_training.py
                                      :220-227); only gt / gt_off cross the bus */
 
+/* Shape of the matching kernel's work list, a per-call option like the detect kernels' cluster width (results never depend
+ * on it): the first coarse_pct % of the prior tiles (coarse pyramid levels first) are paired with GT segments of seg_a rows,
+ * the remaining tiles with segments of seg_b rows; 16 <= seg <= 192.  No JABD_ASSIGN_TUNE bits: the library's choice -- 64 for
+ * a call that runs alone (short items: short tail), 192 for batches that overlap on the lanes of jabd_assign_batches (fewer
+ * items: less per-item work). */
+#define JABD_ASSIGN_TUNE(seg_a, seg_b, coarse_pct) (((seg_a) << 8) | ((seg_b) << 16) | ((coarse_pct) << 24))
+
 JABD_API int jabd_version(void);
 JABD_API const char *jabd_last_error(void);
 /* Fills SM count and compute capability of the current device.  Synchronous, host only. */
@@ -121,7 +128,8 @@ JABD_API int jabd_assign(const float *priors, int64_t P, const float *gt, const 
  * ramp and tail (cfg2: 27 us per batch instead of 33).  Every lane is ordered after `stream` at entry and `stream` after
  * every lane at exit (events; nothing synchronises the host), so to the caller this behaves like n_batches jabd_assign calls
  * on `stream`; it may be captured into a CUDA graph through `stream`.  n_lanes == 0: the batches run back to back on
- * `stream`.  Every batch needs its own outputs and its own workspace; `priors` and the scalar options are shared. */
+ * `stream`.  Batches on different lanes need their own outputs and workspaces (one lane is stream-ordered: a batch may reuse
+ * the buffers of an earlier one there); `priors` and the scalar options are shared. */
 typedef struct {
     const float *gt;      /* [sumG,15] */
     const int *gt_off;    /* [B+1] */

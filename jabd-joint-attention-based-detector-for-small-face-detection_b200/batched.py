@@ -58,8 +58,19 @@ def pack_targets(targets, device):
     return gt, offs, offs_host
 
 
+def tune_flags(tune):
+    """``JABD_ASSIGN_TUNE(seg_a, seg_b, coarse_pct)``: shape of the matching kernel's work list (a per-call option, results do
+    not depend on it); ``None``: the library's choice."""
+    if tune is None:
+        return 0
+    a, b, pct = (int(x) for x in tune)
+    if not (0 < a < 256 and 0 < b < 256 and 0 <= pct <= 100):
+        raise ValueError("tune must be (seg_a, seg_b, coarse_pct)")
+    return (a << 8) | (b << 16) | (pct << 24)
+
+
 def assign_targets(priors, targets, threshold=0.35, variances=(0.1, 0.2), label_mode=0, encode=True, dense=False,
-                   with_landm=True, return_match=False, allow_empty=False, out=None):
+                   with_landm=True, return_match=False, allow_empty=False, out=None, tune=None):
     """Target assignment for a batch.
 
     priors   [P,4] (cx,cy,w,h); targets: see ``pack_targets``.
@@ -102,7 +113,7 @@ def assign_targets(priors, targets, threshold=0.35, variances=(0.1, 0.2), label_
     ws = _tensor.workspace(L.jabd_assign_workspace_bytes(B, P, sumG), dev)
     with torch.cuda.device(dev):
         _lib.call("jabd_assign", ptr(pri), P, ptr(gt), ptr(offs), B, sumG, float(threshold), v0, v1, int(label_mode),
-                  1 if encode else 0, FLAG_DENSE if dense else 0, ptr(loc_t), ptr(conf_t), ptr(landm_t), ptr(bti), ptr(bto),
+                  1 if encode else 0, (FLAG_DENSE if dense else 0) | tune_flags(tune), ptr(loc_t), ptr(conf_t), ptr(landm_t), ptr(bti), ptr(bto),
                   ptr(bpi), ptr(bpo), ptr(ws), ws.numel(), _tensor.stream_of(dev))
     if return_match:
         return loc_t, conf_t, landm_t, extra
@@ -133,7 +144,7 @@ class AssignBatches(object):
     """
 
     def __init__(self, priors, batches, threshold=0.35, variances=(0.1, 0.2), label_mode=0, encode=True, dense=False,
-                 with_landm=True, lanes_n=4, device=None):
+                 with_landm=True, lanes_n=4, device=None, tune=None):
         first = batches[0] if len(batches) else None
         dev = device or _tensor.device_of(priors, first[0] if isinstance(first, (list, tuple)) and len(first) else None)
         self.dev = torch.device(dev)
@@ -142,7 +153,7 @@ class AssignBatches(object):
             raise ValueError("priors must be [P, 4]")
         self.P = int(self.pri.shape[0])
         self.opts = (float(threshold),) + _tensor.variances_of(variances) + (int(label_mode), 1 if encode else 0,
-                                                                             FLAG_DENSE if dense else 0)
+                                                                             (FLAG_DENSE if dense else 0) | tune_flags(tune))
         L = _lib.lib()
         self.items, self.outputs = [], []
         arr = (_lib.AssignBatch * max(len(batches), 1))()

@@ -47,12 +47,19 @@
 namespace jabd {
 
 constexpr int kTile = 256;       // priors per work item, one per thread
-#ifndef JABD_KSEG
-#define JABD_KSEG 64
-#endif
-constexpr int kSeg = JABD_KSEG;  // GT per work item (bounds the longest per-warp dependency chain)
+// GT per work item.  A run-time choice per call (AssignTune): small segments bound the longest per-warp dependency chain and
+// the backlog a CTA can sit on when the queue runs dry -- what a launch running ALONE ends on --, large ones mean fewer items,
+// i.e. fewer culling ballots, staging round trips and column-key atomics per pair -- what counts when other launches fill the
+// tail anyway (jabd_assign_batches).  The work list has two regimes: the first `coarse_tiles` tiles of the processing order
+// (coarse pyramid levels first) are cut into segments of `seg_a`, the remaining tiles into segments of `seg_b`.
+constexpr int kSegMax = 192;     // shared-memory capacity of a stage; hit lists hold GT indices as bytes (< 256)
+constexpr int kSegMin = 16;      // work-list capacity is sized for this
+constexpr int kSegDefault = 64;
 constexpr int kWide = 4;         // GT hits processed per step by a warp
-constexpr int kMatchCtasPerSm = 4;
+#ifndef JABD_MATCH_CTAS
+#define JABD_MATCH_CTAS 4
+#endif
+constexpr int kMatchCtasPerSm = JABD_MATCH_CTAS;
 #ifndef JABD_KSTAGES
 #define JABD_KSTAGES 2
 #endif
@@ -87,8 +94,15 @@ struct AssignWorkspace {
     unsigned long long *colkey; // [B,P]  best GT per prior before the force-match override (0 = value +0 at GT 0)
     float4 *wbox;               // [n_tiles*8] bounding box of each warp's 32 priors (point form)
     int *tile_ok;               // [n_tiles] every prior area of the tile within [2^-40, 2^40]
-    int4 *segs;                 // work list: (image, first GT within the image, count, record offset)
-    int *ctl;                   // [0] number of segments, [1] work-queue head
+    int4 *segs;                 // work list, regime A: (image, first GT within the image, count, record offset)
+    int4 *segs_b;               // regime B
+    int *ctl;                   // [0] segments in list A, [1] work-queue head, [2] segments in list B
+};
+
+// Per-call shape of the work list (see kSegMax): results never depend on it.
+struct AssignTune {
+    int seg_a, seg_b;   // GT per item in the two regimes, kSegMin..kSegMax
+    int coarse_pct;     // share of the tiles (processing order: coarse levels first) that use seg_a, 0..100
 };
 
 static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *w, char *base)
@@ -101,7 +115,7 @@ static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *
     };
     const size_t ng = (size_t)(sumG > 0 ? sumG : 1);
     const size_t nt = (size_t)((P + kTile - 1) / kTile) + 1;
-    const size_t nseg = (size_t)(B > 0 ? B : 0) + (size_t)(sumG > 0 ? sumG : 0) / kSeg + 1;
+    const size_t nseg = (size_t)(B > 0 ? B : 0) + (size_t)(sumG > 0 ? sumG : 0) / kSegMin + 1;
     size_t o_rec = take(sizeof(GtRec) * ng);
     size_t o_enc = take(sizeof(EncRec) * ng);
     size_t o_row = take(sizeof(unsigned long long) * ng);
@@ -109,6 +123,7 @@ static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *
     size_t o_wbox = take(sizeof(float4) * nt * (kTile / 32));
     size_t o_tiles = take(sizeof(int) * nt);
     size_t o_segs = take(sizeof(int4) * nseg);
+    size_t o_segs_b = take(sizeof(int4) * nseg);
     size_t o_ctl = take(sizeof(int) * 4);
     if (w) {
         w->gtrec = reinterpret_cast<GtRec *>(base + o_rec);
@@ -118,6 +133,7 @@ static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *
         w->wbox = reinterpret_cast<float4 *>(base + o_wbox);
         w->tile_ok = reinterpret_cast<int *>(base + o_tiles);
         w->segs = reinterpret_cast<int4 *>(base + o_segs);
+        w->segs_b = reinterpret_cast<int4 *>(base + o_segs_b);
         w->ctl = reinterpret_cast<int *>(base + o_ctl);
     }
     return off;
@@ -127,7 +143,7 @@ static size_t assign_ws_layout(int B, int64_t P, int64_t sumG, AssignWorkspace *
 // blockIdx.x < B: image role; < B + n_tiles: tile role; == B + n_tiles: scan role.
 __global__ void __launch_bounds__(kTile) assign_prep_kernel(const float *__restrict__ gt, const int *__restrict__ gt_off,
                                                             const float4 *__restrict__ priors, int P, int B, int n_tiles,
-                                                            int queue_head, AssignWorkspace ws)
+                                                            int queue_head, AssignWorkspace ws, int seg_a, int seg_b)
 {
     __shared__ int s_scan[kTile / 32];
     const int tid = threadIdx.x;
@@ -202,37 +218,42 @@ __global__ void __launch_bounds__(kTile) assign_prep_kernel(const float *__restr
             for (int b = 0; b < B; ++b) ws.colkey[(size_t)b * P + p] = 0ull;
         return;
     }
-    // ---- scan role: segment list in image order
-    int running = 0;
-    for (int base = 0; base < B; base += kTile) {
-        const int b = base + tid;
-        int g0 = 0, G = 0;
-        if (b < B) { g0 = gt_off[b]; G = gt_off[b + 1] - g0; }
-        const int c = G > 0 ? (G + kSeg - 1) / kSeg : 0;
-        int incl = c;
+    // ---- scan role: the two segment lists in image order (list B only if some tile uses it: seg_b > 0)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int seg = pass == 0 ? seg_a : seg_b;
+        int4 *list = pass == 0 ? ws.segs : ws.segs_b;
+        int running = 0;
+        for (int base = 0; seg > 0 && base < B; base += kTile) {
+            const int b = base + tid;
+            int g0 = 0, G = 0;
+            if (b < B) { g0 = gt_off[b]; G = gt_off[b + 1] - g0; }
+            const int c = G > 0 ? (G + seg - 1) / seg : 0;
+            int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(kFull, incl, o);
-            if ((int)lane >= o) incl += v;
-        }
-        if (lane == 31) s_scan[warp] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            int before = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < kTile / 32; ++w) {
-            const int v = s_scan[w];
-            if (w < warp) before += v;
-            total += v;
+            for (int w = 0; w < kTile / 32; ++w) {
+                const int v = s_scan[w];
+                if (w < warp) before += v;
+                total += v;
+            }
+            const int first = running + before + incl - c;
+            for (int k = 0; k < c; ++k) {
+                const int c0 = k * seg;
+                list[first + k] = make_int4(b, c0, (G - c0) < seg ? (G - c0) : seg, g0 + c0);
+            }
+            running += total;
+            __syncthreads();
         }
-        const int first = running + before + incl - c;
-        for (int k = 0; k < c; ++k) {
-            const int c0 = k * kSeg;
-            ws.segs[first + k] = make_int4(b, c0, (G - c0) < kSeg ? (G - c0) : kSeg, g0 + c0);
-        }
-        running += total;
-        __syncthreads();
+        if (tid == 0) ws.ctl[pass == 0 ? 0 : 2] = running;
     }
-    if (tid == 0) { ws.ctl[0] = running; ws.ctl[1] = queue_head; }
+    if (tid == 0) ws.ctl[1] = queue_head;
 }
 
 // -------------------------------------------------------------------------------------------------------
@@ -273,7 +294,7 @@ struct ItemMeta {
 };
 
 struct MatchSmem {
-    GtRec gt[kStages][kSeg + 1];      // bulk-copy destinations (kStages x 2 KB); record kSeg of every stage is the null GT
+    GtRec gt[kStages][kSegMax + 1];   // bulk-copy destinations (kStages x 6 KB); record kSegMax of every stage is the null GT
                                       // (an inverted box far away: zero intersection with everything), never overwritten
     float4 pri[kStages][kTile];       //                        (kStages x 4 KB)
     float4 wbox[kStages][kTile / 32]; //                        (kStages x 128 B)
@@ -283,8 +304,8 @@ struct MatchSmem {
     uint32_t hits[kTile / 32][12];    // per consumer warp: the GT of the current 32-GT group that hit its bounding box, one
                                       // byte each, padded with the null GT to a multiple of four (<= 36 bytes used)
 };
-constexpr int kNullGt = kSeg;         // index of the null GT record of a stage
-static_assert(kSeg + 1 <= 256, "hit lists hold GT indices as bytes");
+constexpr int kNullGt = kSegMax;      // index of the null GT record of a stage
+static_assert(kSegMax + 1 <= 256, "hit lists hold GT indices as bytes");
 
 // One GT segment against the warp's 32 priors.  MODE 0: culled (ballot of 32 GT against the warp's bounding box),
 // MODE 1: dense, MODE 2: dense with torch.max's NaN / ordering semantics (malformed input).
@@ -369,13 +390,15 @@ __device__ __forceinline__ void consume_segment(const GtRec *__restrict__ rec, i
 
 __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_kernel(const float4 *__restrict__ priors, int P,
                                                                                       AssignWorkspace ws, int dense,
-                                                                                      int n_tiles)
+                                                                                      int n_tiles, int coarse_tiles)
 {
     __shared__ __align__(128) MatchSmem s;
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int n_seg = ws.ctl[0];
-    const long long n_items = (long long)n_seg * n_tiles;
+    // items 0 .. items_a-1: the first coarse_tiles tiles of the processing order x list A; then the other tiles x list B
+    const int n_seg_a = ws.ctl[0], n_seg_b = ws.ctl[2];
+    const long long items_a = (long long)n_seg_a * coarse_tiles;
+    const long long n_items = items_a + (long long)n_seg_b * (n_tiles - coarse_tiles);
 
     int all_ok = 1;
     for (int t = tid; t < n_tiles; t += kMatchThreads) all_ok &= ws.tile_ok[t];
@@ -410,8 +433,17 @@ __global__ void __launch_bounds__(kMatchThreads, kMatchCtasPerSm) assign_match_k
                 mbar_arrive(&s.full[slot]);
                 return;
             }
-            const int4 seg = ws.segs[item % n_seg];
-            const int tile = n_tiles - 1 - (int)(item / n_seg); // coarse pyramid levels (last tiles) first
+            int4 seg;
+            int tile_ord;
+            if (item < items_a) {
+                seg = ws.segs[item % n_seg_a];
+                tile_ord = (int)(item / n_seg_a);
+            } else {
+                const long long it = item - items_a;
+                seg = ws.segs_b[it % n_seg_b];
+                tile_ord = coarse_tiles + (int)(it / n_seg_b);
+            }
+            const int tile = n_tiles - 1 - tile_ord; // coarse pyramid levels (last tiles) first
             const int np = (P - tile * kTile) < kTile ? (P - tile * kTile) : kTile;
             m.tile = tile; m.image = seg.x; m.c0 = seg.y; m.n = seg.z; m.rec0 = seg.w;
             s.meta[slot] = m;
@@ -758,6 +790,25 @@ static int check_assign_common(const float *priors, int64_t P, const float *gt, 
     return JABD_OK;
 }
 
+// JABD_ASSIGN_TUNE(seg_a, seg_b, coarse_pct) in bits 8..30 of a call's flags; all-zero bits: the default shape of a call
+// that runs alone (see kSegMax).
+static int assign_tune_of(int flags, AssignTune *t)
+{
+    const int a = (flags >> 8) & 255, b = (flags >> 16) & 255, pct = (flags >> 24) & 127;
+    if (a == 0 && b == 0 && pct == 0) {
+        t->seg_a = kSegDefault;
+        t->seg_b = kSegDefault;
+        t->coarse_pct = 100;
+        return JABD_OK;
+    }
+    JABD_REQUIRE(a >= kSegMin && a <= kSegMax && b >= kSegMin && b <= kSegMax && pct <= 100, JABD_EINVAL,
+                 "assign: JABD_ASSIGN_TUNE(seg_a, seg_b, coarse_pct) needs %d <= seg <= %d and 0 <= coarse_pct <= 100", kSegMin, kSegMax);
+    t->seg_a = a;
+    t->seg_b = b;
+    t->coarse_pct = pct;
+    return JABD_OK;
+}
+
 } // namespace jabd
 
 using namespace jabd;
@@ -774,6 +825,9 @@ int jabd_assign_match(const float *priors, int64_t P, const float *gt, const int
                       void *workspace, size_t workspace_bytes, jabd_stream_t stream)
 {
     int rc = check_assign_common(priors, P, gt, gt_off, B, sumG, workspace, workspace_bytes);
+    if (rc != JABD_OK) return rc;
+    AssignTune tune;
+    rc = assign_tune_of(flags, &tune);
     if (rc != JABD_OK || B == 0 || P == 0) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     AssignWorkspace ws;
@@ -783,16 +837,20 @@ int jabd_assign_match(const float *priors, int64_t P, const float *gt, const int
     JABD_CUDA(cudaGetDevice(&dev));
     JABD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // persistent grid: one CTA per resident slot, never more than there can be work items
-    const long long max_items = (long long)n_tiles * ((long long)B + sumG / kSeg);
+    const int coarse_tiles = (int)(((long long)n_tiles * tune.coarse_pct + 99) / 100);
+    const int seg_small = coarse_tiles == 0 ? tune.seg_b
+                                            : (coarse_tiles == (int)n_tiles || tune.seg_a < tune.seg_b ? tune.seg_a : tune.seg_b);
+    const long long max_items = (long long)n_tiles * ((long long)B + sumG / seg_small);
     long long grid = (long long)sms * kMatchCtasPerSm;
     grid = grid < max_items ? grid : max_items;
     grid = grid < 1 ? 1 : grid;
     assign_prep_kernel<<<(unsigned)B + n_tiles + 1u, kTile, 0, st>>>(gt, gt_off, reinterpret_cast<const float4 *>(priors), (int)P, B,
-                                                                     (int)n_tiles, (int)grid, ws);
+                                                                     (int)n_tiles, (int)grid, ws, coarse_tiles > 0 ? tune.seg_a : 0,
+                                                                     coarse_tiles < (int)n_tiles ? tune.seg_b : 0);
     JABD_LAUNCH_CHECK("assign_prep_kernel");
     if (flags & JABD_ASSIGN_PREP_ONLY) return JABD_OK;
     assign_match_kernel<<<(unsigned)grid, kMatchThreads, 0, st>>>(reinterpret_cast<const float4 *>(priors), (int)P, ws,
-                                                          (flags & JABD_ASSIGN_DENSE) ? 1 : 0, (int)n_tiles);
+                                                          (flags & JABD_ASSIGN_DENSE) ? 1 : 0, (int)n_tiles, coarse_tiles);
     JABD_LAUNCH_CHECK("assign_match_kernel");
     return JABD_OK;
 }
@@ -866,6 +924,7 @@ int jabd_assign_batches(const float *priors, int64_t P, const jabd_assign_batch_
         JABD_REQUIRE(lanes[l] != stream, JABD_EINVAL, "assign_batches: lane %d is the calling stream", l);
         for (int m = 0; m < l; ++m) JABD_REQUIRE(lanes[l] != lanes[m], JABD_EINVAL, "assign_batches: lanes %d and %d are the same stream", m, l);
     }
+    const int used = n_lanes < n_batches ? n_lanes : n_batches;
     // everything that can be refused is refused before the first lane is forked
     for (int i = 0; i < n_batches; ++i) {
         const jabd_assign_batch_t &b = batches[i];
@@ -875,11 +934,11 @@ int jabd_assign_batches(const float *priors, int64_t P, const jabd_assign_batch_
         JABD_REQUIRE(b.loc_t && b.conf_t, JABD_EINVAL, "assign_batches: batch %d: loc_t/conf_t must not be null", i);
         JABD_REQUIRE(aligned_to(b.loc_t, 16) && aligned_to(b.conf_t, 8) && aligned_to(b.landm_t, 4), JABD_EALIGN,
                      "assign_batches: batch %d: loc_t needs 16-byte, conf_t 8-byte, landm_t 4-byte alignment", i);
+        // the same workspace twice is fine on one lane (stream order), a race on two
         for (int j = 0; j < i; ++j)
-            JABD_REQUIRE(batches[j].workspace != b.workspace || batches[j].B == 0, JABD_EINVAL,
-                         "assign_batches: batches %d and %d share a workspace", j, i);
+            JABD_REQUIRE(batches[j].workspace != b.workspace || batches[j].B == 0 || used == 0 || i % used == j % used, JABD_EINVAL,
+                         "assign_batches: batches %d and %d share a workspace on different lanes", j, i);
     }
-    const int used = n_lanes < n_batches ? n_lanes : n_batches;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaEvent_t fork = nullptr;
     if (used > 0) {
@@ -889,6 +948,9 @@ int jabd_assign_batches(const float *priors, int64_t P, const jabd_assign_batch_
         cudaEventDestroy(fork);
         if (e != cudaSuccess) return cuda_fail(e, "assign_batches: fork");
     }
+    // batches that overlap on lanes are cut into large items (fewer culling ballots, staging round trips and column-key
+    // atomics per pair; the longer tail of each launch is filled by its neighbours) unless the caller chose a shape itself
+    if (used > 1 && (flags & JABD_ASSIGN_TUNE(255, 255, 127)) == 0) flags |= JABD_ASSIGN_TUNE(kSegMax, kSegMax, 100);
     int rc = JABD_OK;
     for (int i = 0; i < n_batches && rc == JABD_OK; ++i) {
         const jabd_assign_batch_t &b = batches[i];

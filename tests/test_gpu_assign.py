@@ -423,8 +423,35 @@ def test_assign_batches_lanes(mods):
     args = (pri.data_ptr(), plan.P, ctypes.cast(plan.arr, ctypes.c_void_p), 2, THR, 0.1, 0.2, 0, 1, 0)
     assert L.jabd_assign_batches(*args, ctypes.cast(lane, ctypes.c_void_p), 1, ctypes.c_void_p(cur)) == -1
     assert "calling stream" in _lib.last_error()
-    plan.arr[1].workspace = plan.arr[0].workspace
-    assert L.jabd_assign_batches(*args, None, 0, ctypes.c_void_p(cur)) == -1 and "share a workspace" in _lib.last_error()
+    plan.arr[1].workspace = plan.arr[0].workspace                     # fine on one stream (stream order), a race on two lanes
+    two = (ctypes.c_void_p * 2)(*[x.cuda_stream for x in bt.lanes(pri.device, 2)])
+    assert L.jabd_assign_batches(*args, ctypes.cast(two, ctypes.c_void_p), 2, ctypes.c_void_p(cur)) == -1
+    assert "share a workspace" in _lib.last_error()
+
+
+def test_assign_work_list_shapes(mods):
+    """JABD_ASSIGN_TUNE: the matching kernel's work list cut into 16..192 GT per item, in one or two regimes over the tiles --
+    every shape gives the bytes of the default one (checked against the oracle); bad shapes are refused."""
+    bt = mods["batched"]
+    pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(640, 640)).get_anchors()
+    targets = mods["synth"].make_gt_batch(2, 9, (640, 640), first_image=64)
+    targets[4] = torch.cat([targets[4]] * 3)[:500]                                # > 2 x 192 GT in one image, duplicates (ties)
+    tg = [t.cuda() for t in targets]
+    ref = mods["orc"].match_batch(THR, [t.numpy() for t in targets], pri.cpu().numpy(), VAR)
+    want = bt.assign_targets(pri, tg, threshold=THR, variances=VAR, return_match=True)
+    check_assign(want[:3], want[3], ref)
+    for tune in ((192, 192, 100), (16, 16, 100), (128, 32, 70), (32, 192, 50), (64, 17, 0), (191, 64, 1), (100, 100, 99)):
+        for dense in (False, True):
+            got = bt.assign_targets(pri, tg, threshold=THR, variances=VAR, return_match=True, tune=tune, dense=dense)
+            assert all(torch.equal(a, b) for a, b in zip(got[:3], want[:3])), tune
+            assert all(torch.equal(got[3][k], want[3][k]) for k in want[3]), tune
+    for bad in ((8, 64, 100), (64, 200, 100), (64, 64, 101)):
+        with pytest.raises(ValueError):
+            bt.assign_targets(pri, tg, tune=bad)
+    # the lanes of jabd_assign_batches pick the large-item shape themselves: same bytes
+    outs = bt.assign_batches(pri, [tg, tg[:3]], threshold=THR, variances=VAR, lanes_n=2)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(outs[0], want[:3]))
 
 
 def test_errors_are_loud(mods):
