@@ -40,6 +40,7 @@
 // disables culling and evaluates all P*G pairs; tests compare the two bit for bit.  If any prior, or any GT of an
 // image, is malformed (negative or non-finite area) that image takes a generic dense path with torch.max's
 // NaN-wins / first-index semantics.
+#include <atomic>
 #include <cstring>
 
 #include "common.cuh"
@@ -532,11 +533,16 @@ struct EncodeArgs {
 #define JABD_ENC_IMAGES 8
 #endif
 #ifndef JABD_ENC_MINB
-#define JABD_ENC_MINB 1
+#define JABD_ENC_MINB 3
+#endif
+#ifndef JABD_ENC_RECCAP
+#define JABD_ENC_RECCAP 896
 #endif
 constexpr int kEncThreads = JABD_ENC_THREADS;
 constexpr int kEncImages = JABD_ENC_IMAGES;
 constexpr int kEncScan = 4;                   // row keys per thread in flight during the force-match scan
+constexpr int kEncRecCap = JABD_ENC_RECCAP;   // GT records of a CTA's images staged in shared memory (56 KB: three CTAs per SM);
+                                              // what does not fit is read from HBM
 
 struct EncRow {   // the GT a prior is matched with in one image
     float4 e0, e1, e2, e3;   // its EncRec
@@ -646,8 +652,13 @@ __device__ __forceinline__ void encode_store(const EncodeArgs &a, const EncOut &
 }
 
 template <bool kLandm, bool kEncode, bool kExtra>
-__global__ void __launch_bounds__(kEncThreads, JABD_ENC_MINB) match_encode_kernel(EncodeArgs a, AssignWorkspace ws, int B)
+__global__ void __launch_bounds__(kEncThreads, JABD_ENC_MINB) match_encode_kernel(EncodeArgs a, AssignWorkspace ws, int B, int rec_cap)
 {
+    // the 64-byte records of the CTA's images (contiguous in the workspace), brought in by ONE bulk copy while the force-match
+    // scan runs: the gather of a prior's matched record is then a shared-memory read instead of a dependent L2 round trip per image
+    extern __shared__ __align__(128) unsigned char enc_dyn[];
+    EncRec *s_rec = reinterpret_cast<EncRec *>(enc_dyn);
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_off[kEncImages + 1];
     __shared__ int s_forced[kEncImages][kEncThreads];
     __shared__ __align__(16) float s_lm[kLandm ? kEncThreads * 10 : 4];   // 320 per warp
@@ -663,6 +674,7 @@ __global__ void __launch_bounds__(kEncThreads, JABD_ENC_MINB) match_encode_kerne
     const int nb = (B - b0) < kEncImages ? (B - b0) : kEncImages;
 
     if (tid <= kEncImages) s_off[tid] = a.gt_off[b0 + (tid < nb ? tid : nb)];
+    if (tid == 0) mbar_init(&s_bar, 1);
     // column keys (0: no positive IoU, i.e. value +0 at GT 0) of the first two images
     const unsigned long long *ckp = ws.colkey + (size_t)b0 * P + (valid ? p : 0);
     unsigned long long ck0 = ckp[0];
@@ -672,6 +684,16 @@ __global__ void __launch_bounds__(kEncThreads, JABD_ENC_MINB) match_encode_kerne
     EncPrior q;
     q.pr = __ldg(a.priors + (valid ? p : 0));
     __syncthreads();
+    const int rec0 = s_off[0];
+    // staged: what fits, and no more records than half the CTA's lookups (a single 2048^2 image with 1,500 faces is gathered
+    // from HBM as before: 256 lookups do not pay for 96 KB of staging per CTA)
+    int n_staged = s_off[kEncImages] - rec0;
+    n_staged = n_staged < rec_cap ? n_staged : rec_cap;
+    n_staged = n_staged < nb * (kEncThreads / 2) ? n_staged : nb * (kEncThreads / 2);
+    if (tid == 0 && n_staged > 0) {
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)n_staged * 64u);
+        bulk_g2s(s_rec, ws.encrec + rec0, (uint32_t)n_staged * 64u, &s_bar);
+    }
 
     // force-match: best_truth_idx[best_prior_idx[j]] = j for j ascending -> the largest j wins (:129-130).  The row keys of
     // the CTA's images are contiguous; every thread takes kEncScan of them per round, all loads of a round in flight together.
@@ -719,12 +741,16 @@ __global__ void __launch_bounds__(kEncThreads, JABD_ENC_MINB) match_encode_kerne
         const int f = s_forced[i][tid];
         if (f >= 0) { r.idx = f; r.ov = 2.0f; }    // :127
         // (an image without GT: the record belongs to the next image or is the workspace's spare one -- loaded, never used)
-        const float4 *e = reinterpret_cast<const float4 *>(ws.encrec + s_off[i] + r.idx);
-        r.e0 = __ldg(e); r.e1 = __ldg(e + 1); r.e2 = __ldg(e + 2); r.e3 = __ldg(e + 3);
+        const int rel = s_off[i] + r.idx - rec0;
+        if (rel < n_staged) {
+            const float4 *e = reinterpret_cast<const float4 *>(s_rec + rel);
+            r.e0 = e[0]; r.e1 = e[1]; r.e2 = e[2]; r.e3 = e[3];
+        } else {
+            const float4 *e = reinterpret_cast<const float4 *>(ws.encrec + rec0 + rel);
+            r.e0 = __ldg(e); r.e1 = __ldg(e + 1); r.e2 = __ldg(e + 2); r.e3 = __ldg(e + 3);
+        }
         return r;
     };
-    EncRow r0 = fetch(0, ck0), r1 = r0;
-    if (nb > 1) r1 = fetch(1, ck1);
     unsigned long long cka = nb > 2 ? ckp[(size_t)2 * P] : 0ull, ckb = nb > 3 ? ckp[(size_t)3 * P] : 0ull; // images i+2, i+3
 
     auto prior_consts = [&](EncPrior &c) {
@@ -746,25 +772,22 @@ __global__ void __launch_bounds__(kEncThreads, JABD_ENC_MINB) match_encode_kerne
     const int n_valid = (P - wp0) < 32 ? (P - wp0) : 32;
     const bool vec_ok = n_valid == 32 && (reinterpret_cast<uintptr_t>(a.landm_t) & 15u) == 0;
 
-    // Two images per trip; r0 / r1 alternate, no register rotation.  Order within a trip: encode image i, REQUEST the record of
-    // image i+2, only then store image i -- a request queued behind a burst of stores (every warp of the SM stores at about the
-    // same time, and the SM's path to L2 carries 32 bytes per clock) would come back after the next image's arithmetic is done.
+    if (n_staged > 0) mbar_wait(&s_bar, 0u);   // the records have landed (issued before the scan: normally long since)
+    // Two images per trip; the column keys run four images ahead (plain coalesced loads, the only global reads of the loop).
     size_t row = (size_t)b0 * P + p, wrow = (size_t)b0 * P + wp0;
 #pragma unroll 1
     for (int i = 0; i < nb; i += 2) {
-        const EncOut o0 = encode_compute<kLandm, kEncode, kExtra>(a, q, r0, s_off[i + 1] > s_off[i]);
         const unsigned long long ck4 = (i + 4 < nb) ? ckp[(size_t)(i + 4) * P] : 0ull;
         const unsigned long long ck5 = (i + 5 < nb) ? ckp[(size_t)(i + 5) * P] : 0ull;
-        if (i + 2 < nb) r0 = fetch(i + 2, cka);
+        const EncOut o0 = encode_compute<kLandm, kEncode, kExtra>(a, q, fetch(i, ck0), s_off[i + 1] > s_off[i]);
         encode_store<kLandm, kExtra>(a, o0, row, wrow, valid, vec_ok, n_valid, sl, lane);
         if (i + 1 >= nb) break;
         row += P; wrow += P;
-        const EncOut o1 = encode_compute<kLandm, kEncode, kExtra>(a, q, r1, s_off[i + 2] > s_off[i + 1]);
-        if (i + 3 < nb) r1 = fetch(i + 3, ckb);
+        const EncOut o1 = encode_compute<kLandm, kEncode, kExtra>(a, q, fetch(i + 1, ck1), s_off[i + 2] > s_off[i + 1]);
         encode_store<kLandm, kExtra>(a, o1, row, wrow, valid, vec_ok, n_valid, sl, lane);
         row += P; wrow += P;
-        cka = ck4;
-        ckb = ck5;
+        ck0 = cka; ck1 = ckb;
+        cka = ck4; ckb = ck5;
     }
 }
 
@@ -787,6 +810,21 @@ static int check_assign_common(const float *priors, int64_t P, const float *gt, 
     const size_t need = assign_ws_layout(B, P, sumG, nullptr, nullptr);
     JABD_REQUIRE(workspace_bytes >= need, JABD_EWORKSPACE, "assign: workspace too small (%zu < %zu bytes)", workspace_bytes,
                  need);
+    return JABD_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize for one instantiation of the encode kernel, once per device (a memo of a device
+// property, like detect.cu's: a race only repeats an idempotent runtime call)
+template <typename K>
+static int enc_smem_optin(K kernel, int variant)
+{
+    static std::atomic<bool> done[8][64];
+    int dev = 0;
+    JABD_CUDA(cudaGetDevice(&dev));
+    const bool memo = dev >= 0 && dev < 64 && variant >= 0 && variant < 8;
+    if (memo && done[variant][dev].load(std::memory_order_acquire)) return JABD_OK;
+    JABD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEncRecCap * sizeof(EncRec))));
+    if (memo) done[variant][dev].store(true, std::memory_order_release);
     return JABD_OK;
 }
 
@@ -888,16 +926,26 @@ int jabd_assign_encode(const float *priors, int64_t P, const float *gt, const in
     const dim3 grid((unsigned)((P + kEncThreads - 1) / kEncThreads), (unsigned)((B + kEncImages - 1) / kEncImages));
     const bool extra = label_mode != 0 || best_truth_idx || best_truth_overlap || best_prior_idx || best_prior_overlap;
     const int variant = (landm_t ? 4 : 0) | (encode_mode ? 2 : 0) | (extra ? 1 : 0);
+    // shared-memory staging of the GT records: as many as the call has, at most kEncRecCap (opt-in above 48 KB, once per device)
+    const int rec_cap = (int)(sumG < kEncRecCap ? sumG : kEncRecCap);
+    const size_t dyn = (size_t)rec_cap * sizeof(EncRec);
+#define JABD_ENC_LAUNCH(L_, E_, X_)                                                                                   \
+    do {                                                                                                              \
+        rc = enc_smem_optin(match_encode_kernel<L_, E_, X_>, variant);                                                \
+        if (rc == JABD_OK) match_encode_kernel<L_, E_, X_><<<grid, kEncThreads, dyn, st>>>(a, ws, B, rec_cap);         \
+    } while (0)
     switch (variant) {
-    case 0: match_encode_kernel<false, false, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
-    case 1: match_encode_kernel<false, false, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
-    case 2: match_encode_kernel<false, true, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
-    case 3: match_encode_kernel<false, true, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
-    case 4: match_encode_kernel<true, false, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
-    case 5: match_encode_kernel<true, false, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
-    case 6: match_encode_kernel<true, true, false><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
-    default: match_encode_kernel<true, true, true><<<grid, kEncThreads, 0, st>>>(a, ws, B); break;
+    case 0: JABD_ENC_LAUNCH(false, false, false); break;
+    case 1: JABD_ENC_LAUNCH(false, false, true); break;
+    case 2: JABD_ENC_LAUNCH(false, true, false); break;
+    case 3: JABD_ENC_LAUNCH(false, true, true); break;
+    case 4: JABD_ENC_LAUNCH(true, false, false); break;
+    case 5: JABD_ENC_LAUNCH(true, false, true); break;
+    case 6: JABD_ENC_LAUNCH(true, true, false); break;
+    default: JABD_ENC_LAUNCH(true, true, true); break;
     }
+#undef JABD_ENC_LAUNCH
+    if (rc != JABD_OK) return rc;
     JABD_LAUNCH_CHECK("match_encode_kernel");
     return JABD_OK;
 }
