@@ -314,6 +314,26 @@ JABD_API int jabd_detect(const float *loc, const float *conf, const float *landm
  * Synchronises `stream` before returning.  Pinned (page-locked, hence device-mapped) loc_host / landm_host are not
  * uploaded: the kernel reads the loc rows of the <= pre_nms_topk candidates and the landmark rows of the <= keep_cap kept
  * detections directly from host memory (conf is always copied: every score is scanned); pageable memory is copied. */
+/* Several independent batches in one call, batch i on lanes[i % n_lanes] (same lane protocol as jabd_assign_batches: caller-
+ * owned side streams, forked from and joined into `stream` by events, capturable; n_lanes == 0: back to back on `stream`).
+ * What changes against n_batches jabd_detect calls is the automatic cluster width: it is chosen for all the images that
+ * are in flight together, i.e. narrower -- one SM per image does the least redundant work, and the other lanes' images keep
+ * the remaining SMs busy.  Batches on different lanes need their own outputs and workspaces; `priors`, thresholds and
+ * `keep_cap` are shared.  Rows, counts and keep lists are those of jabd_detect. */
+typedef struct {
+    const float *loc;     /* [B,P,4] */
+    const float *conf;    /* [B,P,2] */
+    const float *landm;   /* [B,P,10] or NULL */
+    int B;
+    float *dets;          /* [B,keep_cap,15] */
+    int *counts;          /* [B] */
+    int *keep_idx;        /* [B,keep_cap] */
+    void *workspace;      /* jabd_detect_workspace_bytes(B, P, keep_cap) */
+    size_t workspace_bytes;
+} jabd_detect_batch_t;
+JABD_API int jabd_detect_batches(const float *priors, int64_t P, const jabd_detect_batch_t *batches_host, int n_batches, float var0,
+                                 float var1, float conf_thres, int thresh_mode, int pre_nms_topk, double nms_thres, int keep_cap,
+                                 int flags, const jabd_stream_t *lanes_host, int n_lanes, jabd_stream_t stream);
 JABD_API size_t jabd_detect_host_scratch_bytes(int B, int64_t P, int keep_cap, int with_landm);
 JABD_API int jabd_detect_host(const float *loc_host, const float *conf_host, const float *landm_host,
                               const float *priors_dev, int B, int64_t P, float var0, float var1, float conf_thres,

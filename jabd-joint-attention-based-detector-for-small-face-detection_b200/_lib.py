@@ -22,6 +22,12 @@ class AssignBatch(ctypes.Structure):
                 ("landm_t", c_vp), ("workspace", c_vp), ("workspace_bytes", c_sz)]
 
 
+class DetectBatch(ctypes.Structure):
+    """``jabd_detect_batch_t`` of include/jabd_b200.h (one batch of ``jabd_detect_batches``)."""
+    _fields_ = [("loc", c_vp), ("conf", c_vp), ("landm", c_vp), ("B", c_int), ("dets", c_vp), ("counts", c_vp), ("keep_idx", c_vp),
+                ("workspace", c_vp), ("workspace_bytes", c_sz)]
+
+
 # name -> (restype, argtypes); mirrors include/jabd_b200.h one to one
 SIGNATURES = {
     "jabd_version": (c_int, []),
@@ -75,6 +81,7 @@ SIGNATURES = {
     "jabd_detect_workspace_bytes": (c_sz, [c_int, c_i64, c_int]),
     "jabd_detect": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64, c_int, c_int,
                             c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "jabd_detect_batches": (c_int, [c_vp, c_i64, c_vp, c_int, c_f32, c_f32, c_f32, c_int, c_int, c_f64, c_int, c_int, c_vp, c_int, c_vp]),
     "jabd_detect_host_scratch_bytes": (c_sz, [c_int, c_i64, c_int, c_int]),
     "jabd_detect_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_f32, c_f32, c_f32, c_int, c_int, c_f64,
                                  c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

@@ -17,7 +17,7 @@ import torch
 from . import _lib, _tensor
 from ._tensor import ptr
 
-__all__ = ["assign_targets", "assign_batches", "AssignBatches", "detect", "pack_targets", "assign_targets_host", "detect_host", "multibox_loss", "correct_boxes", "letterbox_params"]
+__all__ = ["assign_targets", "assign_batches", "AssignBatches", "detect_batches", "DetectBatches", "detect", "pack_targets", "assign_targets_host", "detect_host", "multibox_loss", "correct_boxes", "letterbox_params"]
 
 THRESH_NONE, THRESH_GE, THRESH_GT = 0, 1, 2
 FLAG_DENSE = 1
@@ -234,6 +234,66 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
         off = int(L.jabd_nms_stats_offset(B, keep_cap))
         return dets, counts, keep_idx, ws[off:off + 16 * B].view(torch.int32).reshape(B, 4)
     return dets, counts, keep_idx
+
+
+class DetectBatches(object):
+    """Fused detect of several independent batches per call (``jabd_detect_batches``): batch i runs on side stream
+    ``i % lanes`` and the cluster width is chosen for all the images in flight together (narrower than a lone call's: less
+    redundant work per image, the other lanes' images keep the rest of the GPU busy).  The caller's stream is ordered before
+    and after all of them; no host synchronisation; capturable into a CUDA graph.  The reference post-processes one image
+    per call (R/predict.py:167-181); a validation pass over a data set (R/evaluate_utils.py) has many images queued.
+
+    ``plan = DetectBatches(priors, [(loc, conf, landm), ...])`` owns outputs and workspaces; ``plan()`` enqueues everything
+    and returns ``[(dets, counts, keep_idx), ...]`` (the same tensors on every call).  All batches share P and the options.
+    """
+
+    def __init__(self, priors, batches, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000, nms_thres=0.4,
+                 keep_topk=750, cluster=0, lanes_n=4, device=None):
+        first = batches[0][0] if len(batches) else None
+        self.dev = torch.device(device) if device is not None else _tensor.device_of(priors, first)
+        self.pri = _tensor.to_dev(priors, self.dev)
+        if self.pri.ndim != 2 or self.pri.shape[1] != 4:
+            raise ValueError("priors must be [P, 4]")
+        self.P = P = int(self.pri.shape[0])
+        self.keep_cap = keep_cap = int(keep_topk) if keep_topk and keep_topk > 0 else P
+        self.opts = _tensor.variances_of(variances) + (float(conf_thres), THRESH_GT if strict else THRESH_GE,
+                                                        int(pre_nms_topk) if pre_nms_topk else 0, float(nms_thres), keep_cap, int(cluster))
+        L = _lib.lib()
+        self.inputs, self.outputs, self.ws = [], [], []
+        arr = (_lib.DetectBatch * max(len(batches), 1))()
+        for i, (loc, conf, landm) in enumerate(batches):
+            loc_d, conf_d = _tensor.to_dev(loc, self.dev), _tensor.to_dev(conf, self.dev)
+            landm_d = _tensor.to_dev(landm, self.dev) if landm is not None else None
+            B = int(loc_d.shape[0])
+            if tuple(loc_d.shape) != (B, P, 4) or tuple(conf_d.shape) != (B, P, 2) or \
+                    (landm_d is not None and tuple(landm_d.shape) != (B, P, 10)):
+                raise ValueError("DetectBatches: batch %d: expected loc [B,P,4], conf [B,P,2], landm [B,P,10]" % i)
+            dets = torch.empty((B, keep_cap, 15), dtype=torch.float32, device=self.dev)
+            counts = torch.empty((B,), dtype=torch.int32, device=self.dev)
+            keep_idx = torch.empty((B, keep_cap), dtype=torch.int32, device=self.dev)
+            ws = _tensor.workspace(L.jabd_detect_workspace_bytes(B, P, keep_cap), self.dev)
+            self.inputs.append((loc_d, conf_d, landm_d))
+            self.outputs.append((dets, counts, keep_idx))
+            self.ws.append(ws)
+            arr[i] = _lib.DetectBatch(loc_d.data_ptr(), conf_d.data_ptr(), landm_d.data_ptr() if landm_d is not None else None, B,
+                                      dets.data_ptr(), counts.data_ptr(), keep_idx.data_ptr(), ws.data_ptr(), ws.numel())
+        self.n = len(batches)
+        self.arr = arr
+        self.lane_streams = lanes(self.dev, max(0, min(int(lanes_n), self.n)))
+        self.lane_arr = (ctypes.c_void_p * max(len(self.lane_streams), 1))(*[s.cuda_stream for s in self.lane_streams])
+
+    def __call__(self):
+        v0, v1, thr, mode, topk, nms, keep_cap, cluster = self.opts
+        with torch.cuda.device(self.dev):
+            _lib.call("jabd_detect_batches", ptr(self.pri), self.P, ctypes.cast(self.arr, ctypes.c_void_p), self.n, v0, v1, thr, mode,
+                      topk, nms, keep_cap, cluster, ctypes.cast(self.lane_arr, ctypes.c_void_p), len(self.lane_streams),
+                      _tensor.stream_of(self.dev))
+        return self.outputs
+
+
+def detect_batches(priors, batches, **kw):
+    """One-shot form of ``DetectBatches``: ``[(dets, counts, keep_idx), ...]`` for a list of ``(loc, conf, landm)`` batches."""
+    return DetectBatches(priors, batches, **kw)()
 
 
 def letterbox_params(input_shape, image_shapes):

@@ -967,16 +967,13 @@ int jabd_assign_batches(const float *priors, int64_t P, const jabd_assign_batch_
                         int n_lanes, jabd_stream_t stream)
 {
     JABD_REQUIRE(n_batches >= 0 && (n_batches == 0 || batches), JABD_EINVAL, "assign_batches: null batch list or negative count");
-    JABD_REQUIRE(n_lanes >= 0 && n_lanes <= 64 && (n_lanes == 0 || lanes), JABD_EINVAL, "assign_batches: 0..64 lanes, non-null list");
-    for (int l = 0; l < n_lanes; ++l) {
-        JABD_REQUIRE(lanes[l] != stream, JABD_EINVAL, "assign_batches: lane %d is the calling stream", l);
-        for (int m = 0; m < l; ++m) JABD_REQUIRE(lanes[l] != lanes[m], JABD_EINVAL, "assign_batches: lanes %d and %d are the same stream", m, l);
-    }
+    int rc = lanes_check(lanes, n_lanes, stream, "assign_batches");
+    if (rc != JABD_OK) return rc;
     const int used = n_lanes < n_batches ? n_lanes : n_batches;
     // everything that can be refused is refused before the first lane is forked
     for (int i = 0; i < n_batches; ++i) {
         const jabd_assign_batch_t &b = batches[i];
-        int rc = check_assign_common(priors, P, b.gt, b.gt_off, b.B, b.sumG, b.workspace, b.workspace_bytes);
+        rc = check_assign_common(priors, P, b.gt, b.gt_off, b.B, b.sumG, b.workspace, b.workspace_bytes);
         if (rc != JABD_OK) return rc;
         if (b.B == 0 || P == 0) continue;
         JABD_REQUIRE(b.loc_t && b.conf_t, JABD_EINVAL, "assign_batches: batch %d: loc_t/conf_t must not be null", i);
@@ -988,36 +985,18 @@ int jabd_assign_batches(const float *priors, int64_t P, const jabd_assign_batch_
                          "assign_batches: batches %d and %d share a workspace on different lanes", j, i);
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaEvent_t fork = nullptr;
-    if (used > 0) {
-        JABD_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        cudaError_t e = cudaEventRecord(fork, st);
-        for (int l = 0; l < used && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(static_cast<cudaStream_t>(lanes[l]), fork, 0);
-        cudaEventDestroy(fork);
-        if (e != cudaSuccess) return cuda_fail(e, "assign_batches: fork");
-    }
+    rc = lanes_fork(st, lanes, used);
+    if (rc != JABD_OK) return rc;
     // batches that overlap on lanes are cut into large items (fewer culling ballots, staging round trips and column-key
     // atomics per pair; the longer tail of each launch is filled by its neighbours) unless the caller chose a shape itself
     if (used > 1 && (flags & JABD_ASSIGN_TUNE(255, 255, 127)) == 0) flags |= JABD_ASSIGN_TUNE(kSegMax, kSegMax, 100);
-    int rc = JABD_OK;
     for (int i = 0; i < n_batches && rc == JABD_OK; ++i) {
         const jabd_assign_batch_t &b = batches[i];
         rc = jabd_assign(priors, P, b.gt, b.gt_off, b.B, b.sumG, threshold, var0, var1, label_mode, encode_mode, flags, b.loc_t,
                          b.conf_t, b.landm_t, nullptr, nullptr, nullptr, nullptr, b.workspace, b.workspace_bytes,
                          used > 0 ? lanes[i % used] : stream);
     }
-    // join even after a failed launch: a lane forked into a stream capture must come back to it
-    for (int l = 0; l < used; ++l) {
-        cudaEvent_t join = nullptr;
-        cudaError_t e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
-        if (e == cudaSuccess) {
-            e = cudaEventRecord(join, static_cast<cudaStream_t>(lanes[l]));
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, join, 0);
-            cudaEventDestroy(join);
-        }
-        if (e != cudaSuccess && rc == JABD_OK) rc = cuda_fail(e, "assign_batches: join");
-    }
-    return rc;
+    return lanes_join(st, lanes, used, rc);
 }
 
 int64_t jabd_pack_gt_rows(const float *const *rows, const int *counts, int B, float *gt_packed, int64_t capacity_rows, int *gt_off)

@@ -230,6 +230,76 @@ def _margin_check(orc, loc, conf, landm, pn, kidx, counts, dets, params, trials=
     return stable, flips
 
 
+def test_detect_batches_lanes(mods):
+    """jabd_detect_batches: several independent batches on side streams (0, 1, 3, 4 lanes; eagerly, from a side stream and
+    replayed from a CUDA graph; automatic and pinned cluster widths) give, batch by batch, the rows of one jabd_detect call
+    each; the first batch is also checked against the oracle."""
+    import ctypes
+    from jabd_b200 import _lib
+    orc, synth, bt = mods["orc"], mods["synth"], mods["batched"]
+    pri = mods["anchors"].Anchors(mods["cfgs"].cfg_mnet, image_size=(640, 640)).get_anchors()
+    P = pri.shape[0]
+    sizes = (3, 1, 5, 2, 4)
+    batches, first = [], 0
+    for n in sizes:
+        ls, cs, ms = [], [], []
+        for i in range(first, first + n):
+            gt = synth.make_gt(2, i, (640, 640), count=30 + 10 * i)
+            l, c, m = synth.make_preds_clustered(2, i, pri.cpu(), gt, VAR) if i % 3 else synth.make_preds_random(2, i, P)
+            ls.append(l); cs.append(c); ms.append(m)
+        batches.append((torch.stack(ls).cuda(), torch.stack(cs).cuda(), torch.stack(ms).cuda() if n != 2 else None))
+        first += n
+    want = [bt.detect(l, c, m, pri, VAR) for (l, c, m) in batches]
+    loc0, conf0, lm0 = batches[0]
+    boxes = mods["ub"].decode(loc0, pri, VAR).cpu().numpy()
+    for i in range(sizes[0]):
+        e_d, e_i = orc.detect(loc0[i].cpu().numpy(), conf0[i].cpu().numpy(), lm0[i].cpu().numpy(), pri.cpu().numpy(), VAR, 0.02, True,
+                              5000, 0.4, 750, boxes_override=boxes[i])
+        c = int(want[0][1][i])
+        assert c == len(e_i) and np.array_equal(want[0][2][i, :c].cpu().numpy(), e_i) and np.array_equal(want[0][0][i, :c].cpu().numpy(), e_d)
+
+    def same(outs):
+        torch.cuda.synchronize()
+        return all(torch.equal(a, b) for o, w in zip(outs, want) for a, b in zip(o, w))
+
+    def scrub(outs):
+        for o in outs:
+            for t in o:
+                t.fill_(-3)
+
+    for n_lanes, width in ((0, 0), (1, 0), (3, 0), (4, 0), (4, 1), (4, 3), (8, 2)):
+        plan = bt.DetectBatches(pri, batches, VAR, lanes_n=n_lanes, cluster=width)
+        assert same(plan()), (n_lanes, width)
+        scrub(plan.outputs)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            outs = plan()
+            tot = [o[1].sum() for o in outs]
+        s.synchronize()
+        assert [int(x) for x in tot] == [int(w[1].sum()) for w in want]
+        assert same(outs)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            plan()
+        scrub(plan.outputs)
+        g.replay()
+        assert same(plan.outputs), ("graph", n_lanes, width)
+    assert same(bt.detect_batches(pri, batches[:2], variances=VAR, lanes_n=2))
+    # refused before anything is enqueued: a lane equal to the calling stream, a bad cluster width, two lanes on one workspace
+    plan = bt.DetectBatches(pri, batches[:2], VAR, lanes_n=1)
+    L = _lib.lib()
+    cur = torch.cuda.current_stream().cuda_stream
+    lane = (ctypes.c_void_p * 1)(cur)
+    args = (pri.data_ptr(), P, ctypes.cast(plan.arr, ctypes.c_void_p), 2, 0.1, 0.2, 0.02, 2, 5000, 0.4, 750)
+    assert L.jabd_detect_batches(*args, 0, ctypes.cast(lane, ctypes.c_void_p), 1, ctypes.c_void_p(cur)) == -1
+    assert "calling stream" in _lib.last_error()
+    assert L.jabd_detect_batches(*args, 9, None, 0, ctypes.c_void_p(cur)) == -1 and "CTAs per image" in _lib.last_error()
+    plan.arr[1].workspace = plan.arr[0].workspace
+    two = (ctypes.c_void_p * 2)(*[x.cuda_stream for x in bt.lanes(pri.device, 2)])
+    assert L.jabd_detect_batches(*args, 0, ctypes.cast(two, ctypes.c_void_p), 2, ctypes.c_void_p(cur)) == -1
+    assert "share a workspace" in _lib.last_error()
+
+
 @pytest.mark.parametrize("gen", ["A", "B"])
 def test_detect_cfg3_batch_vs_oracle(mods, gen):
     """BASELINE configs[2] at full size: 1024x1024 (43,008 priors), > 0.02, top-5000, IoU 0.4, keep 750."""
