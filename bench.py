@@ -30,7 +30,6 @@ THR = 0.35
 IMAGE = (640, 640)
 BATCH = 32            # images per GPU per step (cfg2; cfg5 = 256 over 8 GPUs)
 LANES = 4             # side streams the steps of one graph are dealt over (jabd_assign_batches): independent batches overlap
-DET_LANES = 4         # side streams of the detect throughput line (jabd_detect_batches)
 DET_SETS = 8          # distinct batches per jabd_detect_batches call
 ROUNDS = 4            # a lanes graph holds ROUNDS x SETS steps (the lanes drain at every graph boundary)
 SETS = 8              # rotating buffer sets: 8 x ~45 MB of outputs+workspace > 126 MB L2
@@ -717,11 +716,11 @@ def main():
                                  "e2e_images_per_s": world * B * n_d / (ms_dh / 1e3), "e2e_h2d_bytes": hd.last_h2d,
                                  "e2e_d2h_bytes": hd.last_d2h, "priors": Pd, "batch": B, "mean_kept": float(out[1].float().mean()),
                                  "params": "score>0.02, top-5000, IoU 0.4, keep 750; clustered synthetic predictions"}
-            # the same detect for DET_SETS distinct batches per call on DET_LANES side streams (jabd_detect_batches): the cluster
-            # width is chosen for all the images in flight, the graph replays one call
+            # the same detect for DET_SETS distinct batches per call (jabd_detect_batches without lanes: ONE launch whose grid covers
+            # the images of all batches, cluster width chosen for all of them); the graph replays one call
             lb = [(loc_d, conf_d, lm_d)] + [tuple(t.to(dev) for t in clustered_preds(3, size, pr, B * j, B, count=60))
                                               for j in range(1, DET_SETS)]
-            plan = batched.DetectBatches(pr, lb, VAR, lanes_n=DET_LANES)
+            plan = batched.DetectBatches(pr, lb, VAR)
             for _ in range(2):
                 outs_l = plan()
             torch.cuda.synchronize(dev)
@@ -730,11 +729,11 @@ def main():
             g_l.replay()
             n_l = 12
             ms_l, _ = timed_loop(lambda k: g_l.replay(), n_l)
-            detect_info[name]["lanes"] = {"images_per_s": world * B * DET_SETS * n_l / (ms_l / 1e3), "ms_per_batch": ms_l / (n_l * DET_SETS),
-                                          "lanes": DET_LANES, "batches_per_call": DET_SETS,
-                                          "what": "batched.DetectBatches -> jabd_detect_batches: %d distinct batches of %d images per call "
-                                                  "dealt over %d side streams, one CUDA graph per call; rows equal jabd_detect's (asserted "
-                                                  "for the first batch)" % (DET_SETS, B, DET_LANES)}
+            detect_info[name]["batches"] = {"images_per_s": world * B * DET_SETS * n_l / (ms_l / 1e3), "ms_per_batch": ms_l / (n_l * DET_SETS),
+                                            "batches_per_call": DET_SETS,
+                                            "what": "batched.DetectBatches -> jabd_detect_batches: %d distinct batches of %d images (own "
+                                                    "inputs, outputs, workspaces) per call in one launch, one CUDA graph per call; rows equal "
+                                                    "jabd_detect's (asserted for the first batch)" % (DET_SETS, B)}
             del plan, lb, g_l
             if cpu_ok:
                 # the reference's per-image post-processing on the host cores (decode, decode_landm, cat, threshold, top-k,

@@ -314,12 +314,14 @@ JABD_API int jabd_detect(const float *loc, const float *conf, const float *landm
  * Synchronises `stream` before returning.  Pinned (page-locked, hence device-mapped) loc_host / landm_host are not
  * uploaded: the kernel reads the loc rows of the <= pre_nms_topk candidates and the landmark rows of the <= keep_cap kept
  * detections directly from host memory (conf is always copied: every score is scanned); pageable memory is copied. */
-/* Several independent batches in one call, batch i on lanes[i % n_lanes] (same lane protocol as jabd_assign_batches: caller-
- * owned side streams, forked from and joined into `stream` by events, capturable; n_lanes == 0: back to back on `stream`).
- * What changes against n_batches jabd_detect calls is the automatic cluster width: it is chosen for all the images that
- * are in flight together, i.e. narrower -- one SM per image does the least redundant work, and the other lanes' images keep
- * the remaining SMs busy.  Batches on different lanes need their own outputs and workspaces; `priors`, thresholds and
- * `keep_cap` are shared.  Rows, counts and keep lists are those of jabd_detect. */
+/* Several independent batches in one call.  n_lanes == 0 (recommended): ONE launch on `stream` whose grid covers the images of
+ * all batches (16 batches per launch; each cluster finds its batch in a table carried by the kernel parameters), so the block
+ * scheduler hands the next image to whichever SM falls free.  n_lanes > 0: batch i is its own launch on lanes[i % n_lanes]
+ * (the lane protocol of jabd_assign_batches: caller-owned side streams, forked from and joined into `stream` by events).
+ * Either way the automatic cluster width is chosen for all the images that are in flight together, i.e. narrower than a lone
+ * call's -- one SM per image does the least redundant work, and the other images keep the remaining SMs busy.  Every batch
+ * needs its own outputs and workspace (two batches on the same lane may share); `priors`, thresholds and `keep_cap` are
+ * shared.  Rows, counts and keep lists are those of jabd_detect.  Capturable. */
 typedef struct {
     const float *loc;     /* [B,P,4] */
     const float *conf;    /* [B,P,2] */

@@ -237,10 +237,11 @@ def detect(loc, conf, landm, priors, variances=(0.1, 0.2), conf_thres=0.02, stri
 
 
 class DetectBatches(object):
-    """Fused detect of several independent batches per call (``jabd_detect_batches``): batch i runs on side stream
-    ``i % lanes`` and the cluster width is chosen for all the images in flight together (narrower than a lone call's: less
-    redundant work per image, the other lanes' images keep the rest of the GPU busy).  The caller's stream is ordered before
-    and after all of them; no host synchronisation; capturable into a CUDA graph.  The reference post-processes one image
+    """Fused detect of several independent batches per call (``jabd_detect_batches``).  ``lanes_n=0`` (default): ONE launch
+    whose grid covers the images of all batches -- the block scheduler hands the next image to whichever SM falls free;
+    ``lanes_n>0``: batch i is its own launch on side stream ``i % lanes``.  Either way the cluster width is chosen for all
+    the images in flight together (narrower than a lone call's: less redundant work per image, the other images keep the
+    rest of the GPU busy).  No host synchronisation; capturable into a CUDA graph.  The reference post-processes one image
     per call (R/predict.py:167-181); a validation pass over a data set (R/evaluate_utils.py) has many images queued.
 
     ``plan = DetectBatches(priors, [(loc, conf, landm), ...])`` owns outputs and workspaces; ``plan()`` enqueues everything
@@ -248,7 +249,7 @@ class DetectBatches(object):
     """
 
     def __init__(self, priors, batches, variances=(0.1, 0.2), conf_thres=0.02, strict=True, pre_nms_topk=5000, nms_thres=0.4,
-                 keep_topk=750, cluster=0, lanes_n=4, device=None):
+                 keep_topk=750, cluster=0, lanes_n=0, device=None):
         first = batches[0][0] if len(batches) else None
         self.dev = torch.device(device) if device is not None else _tensor.device_of(priors, first)
         self.pri = _tensor.to_dev(priors, self.dev)

@@ -34,8 +34,8 @@ for size, B in ((640, 32), (1024, 16)):
         batched.detect(loc, conf, landm, pri, VAR, out=out)
 
     line = []
-    for ns in (1, 2, 4, 8):
-        for width in ((0, 1, 2) if ns == 1 else (1, 2, 3, 4)):
+    for ns in (1, 4, 8):
+        for width in ((0,) if ns == 1 else (1, 2)):
             side = [torch.cuda.Stream(dev) for _ in range(ns - 1)]
 
             def runw(st):
@@ -69,4 +69,23 @@ for size, B in ((640, 32), (1024, 16)):
             ms_ = e0.elapsed_time(e1) / (20 * SETS)
             ok = all(torch.equal(a, b) for (_, _, _, o), r in zip(sets, ref) for a, b in zip(o, r))
             line.append("S=%d C=%s %.3f ms (%.0f img/s)%s" % (ns, width or "auto", ms_, B / ms_ * 1e3, "" if ok else " MISMATCH"))
+    for width in (0, 1, 2):          # jabd_detect_batches without lanes: one launch over the images of all batches
+        plan = batched.DetectBatches(pri, [(l, c, m) for (l, c, m, _) in sets], VAR, lanes_n=0, cluster=width)
+        outs = plan()
+        torch.cuda.synchronize()
+        ok = all(torch.equal(a, b) for o, r in zip(outs, ref) for a, b in zip(o, r))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            plan()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ = e0.elapsed_time(e1) / (20 * SETS)
+        line.append("merged C=%s %.3f ms (%.0f img/s)%s" % (width or "auto", ms_, B / ms_ * 1e3, "" if ok else " MISMATCH"))
     print("%dx%d B=%d: %s" % (size, size, B, "; ".join(line)), flush=True)

@@ -267,7 +267,7 @@ def test_detect_batches_lanes(mods):
             for t in o:
                 t.fill_(-3)
 
-    for n_lanes, width in ((0, 0), (1, 0), (3, 0), (4, 0), (4, 1), (4, 3), (8, 2)):
+    for n_lanes, width in ((0, 0), (0, 1), (0, 3), (1, 0), (3, 0), (4, 0), (4, 1), (4, 3), (8, 2)):   # 0 lanes: all batches in one launch
         plan = bt.DetectBatches(pri, batches, VAR, lanes_n=n_lanes, cluster=width)
         assert same(plan()), (n_lanes, width)
         scrub(plan.outputs)
@@ -298,6 +298,14 @@ def test_detect_batches_lanes(mods):
     two = (ctypes.c_void_p * 2)(*[x.cuda_stream for x in bt.lanes(pri.device, 2)])
     assert L.jabd_detect_batches(*args, 0, ctypes.cast(two, ctypes.c_void_p), 2, ctypes.c_void_p(cur)) == -1
     assert "share a workspace" in _lib.last_error()
+    assert L.jabd_detect_batches(*args, 0, None, 0, ctypes.c_void_p(cur)) == -1 and "share a workspace" in _lib.last_error()
+    # more batches than one launch's table holds (16): 19 batches of one or two images in two launches
+    many = [(loc0[i % 3:i % 3 + 1 + i % 2], conf0[i % 3:i % 3 + 1 + i % 2], lm0[i % 3:i % 3 + 1 + i % 2]) for i in range(19)]
+    got = bt.detect_batches(pri, many, variances=VAR, lanes_n=0)
+    torch.cuda.synchronize()
+    for i, o in enumerate(got):
+        for t, w in zip(o, want[0]):
+            assert torch.equal(t, w[i % 3:i % 3 + 1 + i % 2]), i
 
 
 @pytest.mark.parametrize("gen", ["A", "B"])
