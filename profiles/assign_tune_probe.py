@@ -88,7 +88,8 @@ for s in sets:
 torch.cuda.synchronize()
 ref = [(s["loc"].clone(), s["conf"].clone(), s["landm"].clone()) for s in sets]
 us_prep = us_of(graph(lambda s: match(s, 2)), SETS, 150)
-cases = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]] or [(64, 64, 100), (128, 128, 100), (192, 192, 100), (128, 64, 50), (128, 32, 75)]
+NL = [int(a[8:]) for a in sys.argv[1:] if a.startswith("--lanes=")] or [4]
+cases = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:] if not a.startswith("--")] or [(64, 64, 100), (128, 128, 100), (192, 192, 100), (128, 64, 50), (128, 32, 75)]
 print("prep alone %.2f us" % us_prep, flush=True)
 for a, b, pct in cases:
     fl = (a << 8) | (b << 16) | (pct << 24)
@@ -98,5 +99,25 @@ for a, b, pct in cases:
     serial = us_of(graph(lambda s: assign(s, fl)), SETS, 150)
     ok = all(torch.equal(x, s["loc"]) and torch.equal(y, s["conf"]) and torch.equal(z, s["landm"]) for (x, y, z), s in zip(ref, sets))
     m = us_of(graph(lambda s: match(s, fl)), SETS, 150) - us_prep
-    lanes = us_of(graph(lambda s: assign(s, fl), 4, 4), SETS * 4, 40)
-    print("seg_a %3d seg_b %3d coarse %3d%%: step alone %6.2f us  match alone %6.2f us  4 lanes %6.2f us  equal %s" % (a, b, pct, serial, m, lanes, ok), flush=True)
+    lanes = ["%d lanes %6.2f us" % (nl, us_of(graph(lambda s: assign(s, fl), nl, 4 if SETS % nl == 0 else 1), SETS * (4 if SETS % nl == 0 else 1), 40)) for nl in NL]
+    print("seg_a %3d seg_b %3d coarse %3d%%: step alone %6.2f us  match alone %6.2f us  %s  equal %s" % (a, b, pct, serial, m, "  ".join(lanes), ok), flush=True)
+
+# one call over all 256 images (what merging the batches of a call into one launch trio would give)
+if "--big" in sys.argv:
+    gt, offs, _ = batched.pack_targets(pool, dev)
+    nb, sumG = len(pool), int(gt.shape[0])
+    big = [dict(gt=gt, offs=offs, sumG=sumG, B=nb, ws=_tensor.workspace(L.jabd_assign_workspace_bytes(nb, P, sumG), dev),
+                loc=torch.empty((nb, P, 4), dtype=torch.float32, device=dev), conf=torch.empty((nb, P), dtype=torch.int64, device=dev),
+                landm=torch.empty((nb, P, 10), dtype=torch.float32, device=dev)) for _ in range(2)]
+    for a, b, pct in cases:
+        fl = (a << 8) | (b << 16) | (pct << 24)
+        for s in big:
+            assign(s, fl)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for s in big:
+                assign(s, fl)
+        t = us_of(g, 2 * 8, 40)
+        ok = torch.equal(big[0]["conf"][:32], ref[0][1]) and torch.equal(big[0]["loc"][32:64], ref[1][0])
+        print("one call of 256 images, seg %d/%d/%d: %.2f us per 32 images  equal %s" % (a, b, pct, t, ok), flush=True)

@@ -18,6 +18,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 #    one profiled pass after warm-up (cudaProfilerStart/Stop inside prof_run.py)
 $PROF > $out/${tag}_plain_prof.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:"assign_|match_encode|detect_kernel|decode_kernel|mbl_|wider_eval_kernel" -c 24 \
+    -k regex:"assign_|match_encode|detect_kernel|detect_multi_kernel|decode_kernel|mbl_|wider_eval_kernel" -c 30 \
     -f -o $out/${tag}_full $PROF > $out/${tag}_ncu_full.log 2>&1
 tail -2 $out/${tag}_ncu_full.log

@@ -21,6 +21,8 @@ if what in ("assign", "loss", "all"):
     P = pri.shape[0]
     tg = [t.cuda() for t in synth.make_gt_batch(2, 32, (640, 640))]
     steps.append(("assign", lambda: batched.assign_targets(pri, tg)))
+    # the shape the lanes of jabd_assign_batches run (192-GT work items), serialised by the profiler
+    steps.append(("assign_lanes_shape", lambda: batched.assign_targets(pri, tg, tune=(192, 192, 100))))
 if what in ("loss", "all"):
     raw = [synth.make_logits(2, i, P) for i in range(32)]
     preds = tuple(torch.stack([r[k] for r in raw]).cuda().requires_grad_(True) for k in range(3))
@@ -50,6 +52,17 @@ if what in ("detect", "all"):
         utils_bbox.decode(locb, pri3, VAR)
         return d
     steps.append(("detect", detect_step))
+    # eight batches of 16 in one launch (jabd_detect_batches without lanes)
+    many = [(loc, conf, lm)]
+    for j in range(1, 8):
+        locs, confs, lms = [], [], []
+        for i in range(16 * j, 16 * j + 16):
+            gt = synth.make_gt(3, i, (1024, 1024), count=60)
+            l, c, m = synth.make_preds_clustered(3, i, pri3, gt, VAR, device="cuda")
+            locs.append(l); confs.append(c); lms.append(m)
+        many.append((torch.stack(locs).cuda(), torch.stack(confs).cuda(), torch.stack(lms).cuda()))
+    plan = batched.DetectBatches(pri3, many, VAR)
+    steps.append(("detect_batches", plan))
 if what in ("eval", "all"):
     imgs = [synth.make_eval_image(6, i) for i in range(256)]
     ev = ([im[2] for im in imgs], [im[0] for im in imgs], [im[1][2] for im in imgs])
