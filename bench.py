@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the detect / dense / loss / cfg1 / cfg4 / cfg5 side measurements")
+    ap.add_argument("--only-cfg5", action="store_true", help="of the side measurements keep the cfg5 validation flow only (probing)")
     ap.add_argument("--no-affinity", action="store_true", help="do not bind each rank to its own slice of the host's vCPUs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -537,6 +538,7 @@ def main():
               "match_dense_equiv_tflops": match_tflops, "fp32_peak_measured_tops": fp32_peak, "fp32_peak_nominal_tops": fp32_nominal}
 
     extras = not args.no_extras
+    only5 = bool(getattr(args, "only_cfg5", False))
     if extras:
         # dense (no culling) matching: every one of the P*G pairs evaluated once -> executed-flops figure
         g_dense = phase_graph(lambda s_: phase_match(s_, 1))
@@ -636,7 +638,7 @@ def main():
 
     # ---- the whole MultiBoxLoss.forward + backward on the device (assign -> mining -> sums -> grads)
     loss_info = None
-    if extras:
+    if extras and not only5:
         ds0 = make_set(list(range(BATCH)))
         preds_l = [synth.make_logits(2, i, P) for i in range(BATCH)]
         pl, pc, pm = (torch.stack([q[j] for q in preds_l]).to(dev) for j in range(3))
@@ -687,7 +689,7 @@ def main():
 
     # ---- inference side: decode+top-k+NMS at 640^2 (the metric's second half) and at cfg3's 1024^2
     detect_info = None
-    if extras:
+    if extras and not only5:
         detect_info = {}
         for name, size, B in (("640x640_b32", (640, 640), 32), ("cfg3_1024x1024_b16", (1024, 1024), 16)):
             pr = anchors.cached_priors(config.cfg_mnet, size, dev)
@@ -815,7 +817,7 @@ def main():
         return res
 
     cfg1_info = cfg4_info = None
-    if extras:
+    if extras and not only5:
         cfg1_info = one_image(1, IMAGE, 0, 200, 50)
         cfg1_info["what"] = "BASELINE configs[0]: batch 1, 640x640, 16,800 priors, 50 faces -- latency per call"
         cfg4_info = one_image(4, (2048, 2048), rank, 50, 10)
