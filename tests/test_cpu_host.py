@@ -116,6 +116,55 @@ def test_host_side_validation_without_gpu(lib):
         lib.check(-4, "x")
 
 
+def test_header_is_plain_c_and_structs_match_ctypes(lib, tmp_path):
+    """include/jabd_b200.h compiles as C (gcc, no CUDA headers) and the two batch structs of the multi-batch entry points have the
+    size and field offsets the ctypes mirrors in _lib.py assume; the lane / shape options are refused host-side before any
+    device call."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of this image"
+    src = tmp_path / "abi.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "jabd_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu\n", sizeof(jabd_assign_batch_t), offsetof(jabd_assign_batch_t, sumG), offsetof(jabd_assign_batch_t, loc_t),
+           offsetof(jabd_assign_batch_t, workspace), offsetof(jabd_assign_batch_t, workspace_bytes));
+    printf("%zu %zu %zu %zu %zu\n", sizeof(jabd_detect_batch_t), offsetof(jabd_detect_batch_t, B), offsetof(jabd_detect_batch_t, dets),
+           offsetof(jabd_detect_batch_t, workspace), offsetof(jabd_detect_batch_t, workspace_bytes));
+    printf("%d\n", JABD_ASSIGN_TUNE(192, 64, 70));
+    return 0;
+}
+""")
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().splitlines()
+    A, D = lib.AssignBatch, lib.DetectBatch
+    assert [int(x) for x in out[0].split()] == [ctypes.sizeof(A), A.sumG.offset, A.loc_t.offset, A.workspace.offset, A.workspace_bytes.offset]
+    assert [int(x) for x in out[1].split()] == [ctypes.sizeof(D), D.B.offset, D.dets.offset, D.workspace.offset, D.workspace_bytes.offset]
+    from jabd_b200 import batched
+    assert int(out[2]) == batched.tune_flags((192, 64, 70)) and batched.tune_flags(None) == 0
+    with pytest.raises(ValueError):
+        batched.tune_flags((64, 64, 101))
+    # host-side refusals of the multi-batch calls (no device is touched before them)
+    L = lib.lib()
+    vp = ctypes.c_void_p
+    one = (vp * 1)(vp(0x1000))
+    assert L.jabd_assign_batches(None, 4, None, 1, 0.35, 0.1, 0.2, 0, 1, 0, None, 0, None) == -1          # null batch list
+    assert L.jabd_assign_batches(None, 4, None, 0, 0.35, 0.1, 0.2, 0, 1, 0, None, 65, None) == -1         # too many lanes
+    assert L.jabd_assign_batches(None, 4, None, 0, 0.35, 0.1, 0.2, 0, 1, 0, ctypes.cast(one, vp), 1, vp(0x1000)) == -1
+    assert "calling stream" in lib.last_error()
+    assert L.jabd_detect_batches(None, 4, None, -1, 0.1, 0.2, 0.02, 2, 0, 0.4, 4, 0, None, 0, None) == -1
+    assert L.jabd_detect_batches(None, 4, None, 0, 0.1, 0.2, 0.02, 2, 0, 0.4, 4, 0, None, 0, None) == 0   # nothing to do
+    buf = np.zeros(64, np.float32)
+    p4 = vp(buf.ctypes.data)
+    # a work-list shape outside 16..192 is refused by the call it belongs to
+    assert L.jabd_assign_match(p4, 4, p4, p4, 1, 1, (8 << 8) | (64 << 16) | (100 << 24), p4, 1 << 20, None) in (-1, -2, -3)
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the operators raise instead of computing on the host."""
     if torch.cuda.is_available():
