@@ -8,8 +8,9 @@
 //                       64-byte records (whole row + "fast division is exact" flag) for the encode kernel in the
 //                       workspace, the image's row-argmax keys zeroed.  tile CTAs: per 256-prior tile a sanity flag,
 //                       the bounding box of each of its 8 warps' priors, the column-argmax keys of the tile zeroed
-//                       for every image.  one scan CTA: the work list -- every image's GT cut into segments of <= 64
-//                       (image, first GT, count, record offset) -- and the work-queue head.
+//                       for every image.  one scan CTA: the work list -- every image's GT cut into segments (image, first GT,
+//                       count, record offset) of <= 64 rows, or whatever the call's work-list shape says (AssignTune below:
+//                       two regimes over the tiles, 16..192 rows) -- and the work-queue head.
 //   assign_match_kernel persistent CTAs (4 per SM) pull work items (prior tile, GT segment) from an atomic queue,
 //                       coarse-level tiles first (their large priors intersect most GT and make the longest items).
 //                       One elected thread stages the next item while the eight consumer warps work on the current one:
@@ -29,9 +30,13 @@
 //                       (ordered IoU bits << 32 | ~prior index).
 //                       The largest key is the largest IoU and, among equal IoUs, the lowest index -- torch.max's
 //                       first-maximum rule -- so indices match the reference bit for bit.
-//   match_encode_kernel one CTA per (256-prior tile, 8 consecutive images): force-match scan (:127-130, largest j wins), then per
-//                       image a software pipeline -- unpack the column key, gather the matched GT's 64-byte record, threshold
-//                       (:143), encode (:61-84), coalesced stores -- with the next images' keys and records in flight.
+//   match_encode_kernel one CTA per (256-prior tile, 8 consecutive images): force-match scan (:127-130, largest j wins) while one
+//                       bulk copy brings the images' 64-byte GT records into shared memory, then per image -- unpack the column
+//                       key, read the matched GT's record from shared memory, threshold (:143), encode (:61-84), coalesced
+//                       stores -- with the column keys four images ahead in flight.
+//   jabd_assign_batches several independent batches per call, batch i on caller-owned side stream i % n_lanes (events fork the
+//                       lanes from the caller's stream and join them back): one batch's staging and encode kernels run in the
+//                       ramp and tail of another batch's persistent matching kernel.
 //
 // Why culling is exact: with well-formed inputs (finite coordinates, GT area in [0, 2^40], prior area in
 // [2^-40, 2^40]) every IoU is >= +0 and a pair whose boxes do not intersect has IoU == +0 exactly, which can
