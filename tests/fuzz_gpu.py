@@ -57,9 +57,11 @@ def fuzz_assign(rng, trial):
     thr = float(rng.choice([0.35, 0.2, 0.5]))
     lm, em = int(rng.integers(0, 2)), int(rng.integers(0, 2))
     ref = orc.match_batch(thr, tg, pn, VAR, lm, em)
+    # a random work-list shape (JABD_ASSIGN_TUNE) on every second trial: results must not depend on it
+    tune = None if trial % 2 else (int(rng.integers(16, 193)), int(rng.integers(16, 193)), int(rng.integers(0, 101)))
     for dense in (False, True):
         loc_t, conf_t, landm_t, ex = batched.assign_targets(pri, [cuda(t) for t in tg], threshold=thr, variances=VAR, label_mode=lm,
-                                                            encode=bool(em), return_match=True, dense=dense)
+                                                            encode=bool(em), return_match=True, dense=dense, tune=tune)
         assert np.array_equal(conf_t.cpu().numpy(), ref["conf_t"]), ("conf_t", trial, dense)
         assert np.array_equal(ex["best_truth_idx"].cpu().numpy(), ref["best_truth_idx"]), ("bti", trial, dense)
         assert np.array_equal(ex["best_truth_overlap"].cpu().numpy(), ref["best_truth_overlap"]), ("bto", trial, dense)
@@ -69,6 +71,13 @@ def fuzz_assign(rng, trial):
         fin = np.isfinite(ref["loc_t"])
         assert np.array_equal(np.isfinite(lt), fin), ("loc finite", trial, dense)
         np.testing.assert_allclose(lt[fin], ref["loc_t"][fin], rtol=RTOL, atol=ATOL)
+    if trial % 3 == 0 and B > 1:
+        # the same images as single-image batches on lanes (jabd_assign_batches): the bytes of the one call above
+        outs = batched.assign_batches(pri, [[cuda(t)] for t in tg], threshold=thr, variances=VAR, label_mode=lm, encode=bool(em),
+                                      lanes_n=int(rng.integers(0, 4)))
+        torch.cuda.synchronize()
+        for i, (a, b_, c_) in enumerate(outs):
+            assert torch.equal(a[0], loc_t[i]) and torch.equal(b_[0], conf_t[i]) and torch.equal(c_[0], landm_t[i]), ("lanes", trial, i)
 
 
 def fuzz_nms(rng, trial):
@@ -142,6 +151,14 @@ def fuzz_detect(rng, trial):
     n = int(counts[0])
     assert n == len(e_i) and np.array_equal(kidx[0, :n].cpu().numpy(), e_i), ("detect idx", trial)
     assert np.array_equal(dets[0, :n].cpu().numpy(), e_d), ("detect rows", trial)
+    if trial % 3 == 0:
+        # the image three times as separate batches of one call (jabd_detect_batches: one launch, or lanes): the same rows
+        one = (l.to(dev)[None], c.to(dev)[None], m.to(dev)[None])
+        outs = batched.detect_batches(pri, [one, one, one], variances=VAR, conf_thres=ct, strict=strict, pre_nms_topk=topk, nms_thres=nt,
+                                      keep_topk=keep, lanes_n=int(rng.integers(0, 3)), cluster=int(rng.integers(0, 5)))
+        torch.cuda.synchronize()
+        for o in outs:
+            assert torch.equal(o[1], counts) and torch.equal(o[2], kidx) and torch.equal(o[0], dets), ("detect batches", trial)
 
 
 def fuzz_loss(rng, trial):
