@@ -916,6 +916,59 @@ def main():
                              "NVLink (sharding.PeerGather, three slots, flags + acknowledgements in peer memory, no host sync); 'nccl' = "
                              "all_gather_into_tensor (fallback when peers cannot be mapped).  Batch k+1 is detected while batch k is "
                              "exchanged; serialised_ms_per_step waits for each exchange in line (round 1's flow)"}
+        # The same flow with TWO steps' images per detect launch (jabd_detect_batches: one grid over both batches, narrower clusters,
+        # the block scheduler refills SMs as images finish); every 32-image block is still exchanged on its own, the consumer
+        # runs one double step behind.  A validation pass has its batches queued, so nothing forces one launch per exchange.
+        pair = None
+        try:
+            g2 = sharding.PeerGather(B5, keep5, dev, depth=4)
+            loc5b, conf5b, lm5b = (x.to(dev) for x in clustered_preds(5, size, pr5, (world + rank) * B5, B5, count=40))
+            kidx5b = torch.empty((B5, keep5), dtype=torch.int32, device=dev)
+            wsb = [_tensor.workspace(L.jabd_detect_workspace_bytes(B5, int(pr5.shape[0]), keep5), dev) for _ in range(2)]
+            P5 = int(pr5.shape[0])
+
+            def two(slot_a, slot_b):
+                return (_lib.DetectBatch * 2)(
+                    _lib.DetectBatch(loc5.data_ptr(), conf5.data_ptr(), lm5.data_ptr(), B5, g2.dets(slot_a).data_ptr(),
+                                     g2.counts(slot_a).data_ptr(), kidx5.data_ptr(), wsb[0].data_ptr(), wsb[0].numel()),
+                    _lib.DetectBatch(loc5b.data_ptr(), conf5b.data_ptr(), lm5b.data_ptr(), B5, g2.dets(slot_b).data_ptr(),
+                                     g2.counts(slot_b).data_ptr(), kidx5b.data_ptr(), wsb[1].data_ptr(), wsb[1].numel()))
+            arrs = {(0, 1): two(0, 1), (2, 3): two(2, 3)}
+
+            def dstep(j):
+                sa, sb = (0, 1) if j % 2 == 0 else (2, 3)
+                g2.acquire(sa)
+                g2.acquire(sb)
+                _lib.call("jabd_detect_batches", ptr(pr5), P5, ctypes.cast(arrs[(sa, sb)], ctypes.c_void_p), 2, VAR[0], VAR[1], 0.02, 2, 5000,
+                          0.4, keep5, 0, None, 0, cur_stream())
+                for sl in (sa, sb):
+                    batched.correct_boxes(g2.dets(sl), g2.counts(sl), post5, letterbox=False, to_pixels=True)
+                    g2.launch(sl)
+                if j >= 1:
+                    for sl in ((2, 3) if j % 2 == 0 else (0, 1)):     # the previous double step's two exchanges
+                        g2.result(sl)
+            for j in range(4):
+                dstep(j)
+            g2.result(2); g2.result(3)
+
+            def dbody(j):
+                dstep(j)
+                if j == n5 // 2 - 1:
+                    for sl in ((0, 1) if j % 2 == 0 else (2, 3)):
+                        g2.result(sl)
+            ms_p, _ = timed_loop(dbody, n5 // 2)
+            ga, _ = g2.result(0 if (n5 // 2 - 1) % 2 == 0 else 2)
+            torch.cuda.synchronize(dev)
+            same_rows = bool(torch.equal(ga.reshape(gd.shape), gd))          # the first batch of a pair is the flow's batch: same rows
+            assert g2.status() == 0, "a peer-memory wait timed out in the two-batch flow"
+            pair = {"images_per_s": world * B5 * (n5 // 2) * 2 / (ms_p / 1e3), "ms_per_step": ms_p / ((n5 // 2) * 2),
+                    "same_rows_as_one_batch_per_launch": same_rows, "transport": g2.transport,
+                    "what": "two steps' images (2 x 32, distinct) per jabd_detect_batches launch, each 32-image block scaled and exchanged on "
+                            "its own (PeerGather, four slots), the consumer one double step behind"}
+            del g2
+        except Exception as e:      # reported, never fatal for the bench line
+            pair = {"error": repr(e)[:200]}
+        cfg5_info["two_batches_per_launch"] = pair
         if rank == 0:
             gd2 = gd.reshape(world * B5, keep5, 15).contiguous()
             preds5 = utils_map.dets_to_pred_rows(gd2, gc.reshape(-1).contiguous())
