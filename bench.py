@@ -342,6 +342,10 @@ def main():
         if lanes_n:
             for m in sorted(set(x % (SETS * ROUNDS) for x in (W, K)) - {0}):
                 tails[m] = capture(lambda m=m: assign_batches((ss * ROUNDS)[:m], lanes_n))
+        # first launch of an instantiated graph uploads it to the device: done here, not inside a timed region
+        for g_ in singles + [chunk] + list(tails.values()):
+            g_.replay()
+        torch.cuda.synchronize(dev)
         return singles, chunk, tails
 
     def assign_batches(ss, n_lanes):

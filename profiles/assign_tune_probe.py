@@ -121,3 +121,37 @@ if "--big" in sys.argv:
         t = us_of(g, 2 * 8, 40)
         ok = torch.equal(big[0]["conf"][:32], ref[0][1]) and torch.equal(big[0]["loc"][32:64], ref[1][0])
         print("one call of 256 images, seg %d/%d/%d: %.2f us per 32 images  equal %s" % (a, b, pct, t, ok), flush=True)
+
+# a SHORT burst: one graph of 20 steps on 4 lanes between two device synchronisations (what `bench.py --steps 20` times)
+if "--burst" in sys.argv:
+    import time
+    for a, b, pct in cases:
+        fl = (a << 8) | (b << 16) | (pct << 24)
+        side = [torch.cuda.Stream(dev) for _ in range(3)]
+        for s in sets:
+            assign(s, fl)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cur = torch.cuda.current_stream(dev)
+            for x in side:
+                x.wait_stream(cur)
+            for i, s in enumerate((sets * 3)[:20]):
+                if i % 4 == 0:
+                    assign(s, fl)
+                else:
+                    with torch.cuda.stream(side[i % 4 - 1]):
+                        assign(s, fl)
+            for x in side:
+                cur.wait_stream(x)
+        ts = []
+        for rep in range(12):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / 20)
+        ts.sort()
+        print("burst of 20 steps, seg %d/%d/%d: median %.2f us per step (min %.2f)" % (a, b, pct, ts[len(ts) // 2], ts[0]), flush=True)
